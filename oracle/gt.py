@@ -1,0 +1,50 @@
+"""Oracle: relevance ground truth + full-ranking metrics (TEST INFRASTRUCTURE).
+
+Restates the relevance definition of ``create_gt`` (reference
+``Helpers/contructGT.py:68-81``) and ``compute_ranking_metrics`` (reference
+``Evaluate/retrieval_overlap.py:84-115``) on in-memory arrays.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from .search import cosine_similarity
+
+
+def relevance_lists(query_vals: np.ndarray, query_ids: Sequence[str], gallery_vals: np.ndarray,
+                    gallery_ids: Sequence[str], exclude_self: bool) -> Dict[str, List[str]]:
+    """``contructGT.py:68-81``: gallery item j is relevant to query i iff their multi-hot
+    label vectors share at least one positive; for test->test (``exclude_self``) the
+    query's own position is dropped (``j != i``)."""
+    query_vals = np.asarray(query_vals).astype(int)
+    gallery_vals = np.asarray(gallery_vals).astype(int)
+    out: Dict[str, List[str]] = {}
+    for i, qid in enumerate(query_ids):
+        shared = (gallery_vals & query_vals[i]).sum(axis=1) > 0
+        out[qid] = [gallery_ids[j] for j, keep in enumerate(shared)
+                    if keep and not (exclude_self and j == i)]
+    return out
+
+
+def compute_ranking_metrics(query_embs, gallery_embs, query_labels, gallery_labels, k=1):
+    """``retrieval_overlap.py:84-115``: (MRR over the full ranking, Hit@k, mean Recall@k
+    over ALL gallery items sharing a label).  Vectorised but arithmetically identical."""
+    sim = cosine_similarity(query_embs, gallery_embs)
+    n = sim.shape[1]
+    ar = np.arange(n)
+    rr, recalls, hits = [], [], 0
+    ql = np.asarray(query_labels) == 1
+    gl = np.asarray(gallery_labels) == 1
+    for i in range(sim.shape[0]):
+        idxs = np.lexsort((ar, -sim[i].astype(np.float64)))
+        rel = (gl & ql[i]).any(axis=1)
+        pos = np.nonzero(rel[idxs])[0]
+        rank = int(pos[0]) + 1 if pos.size else None
+        rr.append(1.0 / rank if rank else 0.0)
+        if rank and rank <= k:
+            hits += 1
+        total = int(rel.sum())
+        recalls.append(int(rel[idxs[:k]].sum()) / total if total > 0 else 0.0)
+    return np.mean(rr), hits / sim.shape[0], np.mean(recalls)
