@@ -1,0 +1,173 @@
+/*
+ * mmr_b200.h -- C ABI of the B200-native retrieval hot path.
+ *
+ * Drop-in boundary for ONE path of ppddddpp/multi-modal-retrieval-predict-project:
+ *   gallery similarity search -> top-K -> label/KG rerank -> P@K / Recall@K / nDCG / mAP / MRR.
+ * Every entry point below names the reference interface (file:line under /root/reference)
+ * it replaces.  The reference is pure Python (numpy / sklearn / heapq / pandas); its
+ * "FFI" is therefore a ctypes binding, loaded next to PyTorch, which
+ * supplies device memory and streams.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++ / torch types.
+ *  - Every function returns an int status: 0 = MMR_OK, otherwise an MMR_E* code;
+ *    mmr_last_error() returns a thread-local message.  No exception crosses the boundary.
+ *  - Data pointers may be HOST or DEVICE pointers (detected with
+ *    cudaPointerGetAttributes).  Host inputs are staged to the device inside the call;
+ *    if any OUTPUT pointer is a host pointer the call synchronises `stream` before it
+ *    returns, otherwise it is asynchronous on `stream`.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *  - Row ids are int64 and GLOBAL: local row + the index's `row_offset` (row shards).
+ *  - Ordering rule everywhere: score descending, then row id ascending (the reference's
+ *    np.argsort(...)[::-1] leaves tie order unspecified).
+ *  - There is NO CPU fallback: with no usable sm_100 device every call fails with
+ *    MMR_ENODEV / MMR_ECUDA.
+ */
+#ifndef MMR_B200_H
+#define MMR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMR_ABI_VERSION 1
+
+/* status codes */
+#define MMR_OK        0
+#define MMR_EINVAL    1   /* bad argument (maps to ValueError / RuntimeError in the Python mirror) */
+#define MMR_ECUDA     2   /* CUDA runtime / driver error */
+#define MMR_ENOMEM    3   /* device allocation failed */
+#define MMR_ENODEV    4   /* no sm_100 device */
+#define MMR_EUNSUP    5   /* valid request the kernels do not cover (e.g. K > MMR_MAX_K) */
+
+/* element types */
+#define MMR_F32   0
+#define MMR_BF16  1
+
+/* search algorithm selection */
+#define MMR_ALGO_AUTO  0   /* scan for small query batches, GEMM otherwise */
+#define MMR_ALGO_SCAN  1   /* HBM-streaming scan, CUDA-core fp32 FMA (any storage dtype) */
+#define MMR_ALGO_GEMM  2   /* tcgen05/TMEM bf16 GEMM with fused top-K epilogue (bf16 storage) */
+
+/* mmr_index_create flags */
+#define MMR_FLAG_BORROW 1  /* emb is a device pointer already in storage layout
+                              (dtype_in == dtype_store, row stride == d_pad): use it in place */
+
+#define MMR_MAX_K 1024
+
+typedef struct mmr_index mmr_index;                 /* one gallery row-shard resident in HBM */
+typedef struct mmr_rerank_tables mmr_rerank_tables; /* label bitmasks + KG vectors in HBM   */
+
+int         mmr_abi_version(void);
+const char* mmr_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Gallery.  Replaces RetrievalEngine.__init__ (Retrieval/retrieval.py:24-32): the gallery is
+ * loaded once and stays resident.  `emb` is (n, d) row-major of dtype_in (host or device).
+ * Stored as dtype_store with rows zero-padded to d_pad (multiple of 64 elements) plus one
+ * fp32 inverse L2 norm per row (0 for a zero row, so that zero rows score 0 like sklearn's
+ * normalize() zero-norm rule).  bf16 storage rounds to nearest even; the norm is taken over
+ * the ROUNDED values.  `row_offset` is added to every row id this shard reports.
+ * ------------------------------------------------------------------------------------- */
+int mmr_index_create(mmr_index** out, const void* emb, int64_t n, int32_t d, int32_t dtype_in,
+                     int32_t dtype_store, int64_t row_offset, int32_t device, int32_t flags,
+                     void* stream);
+int mmr_index_destroy(mmr_index* index);
+int mmr_index_info(const mmr_index* index, int64_t* n, int32_t* d, int32_t* d_pad,
+                   int32_t* dtype_store, int32_t* device, int64_t* row_offset, int64_t* hbm_bytes);
+/* device pointers of the stored gallery (n x d_pad) and the inverse norms (n) -- for tests and
+ * roofline accounting; owned by the index. */
+int mmr_index_device_ptrs(const mmr_index* index, const void** emb, const float** inv_norm);
+/* RetrievalEngine.get_embeddings_for_ids (Retrieval/retrieval.py:41-50): gather rows by GLOBAL
+ * row id into `out` (m x d fp32); a row id outside the shard (e.g. -1 = unknown id) yields zeros. */
+int mmr_index_get_rows(const mmr_index* index, const int64_t* rows, int64_t m, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Exact cosine search + top-K.  Replaces the exact form cosine_similarity(Q, G) +
+ * np.argsort(row)[::-1][:k] (Evaluate/retrieval_overlap.py:85,90; Retrieval/retrieval.py:128,134)
+ * and stands in for DLSRetrievalEngine.retrieve (Retrieval/retrieval.py:140-244), whose greedy
+ * walk is approximate.  q is (b, d) of q_dtype.  With a bf16 index the queries are rounded to
+ * bf16 first.  score = (dot(q, g) * inv_norm(g)) * inv_norm(q) accumulated in fp32.
+ * Outputs (b, k): best first; if the shard has fewer than k rows the tail is row = -1,
+ * score = -inf.  `exclude_rows` (b global row ids, may be NULL, -1 = none) removes one row per
+ * query (the np.fill_diagonal(sim, -1) of Retrieval/retrieval.py:129 when building a link graph).
+ * ------------------------------------------------------------------------------------- */
+int mmr_search(mmr_index* index, const void* q, int32_t b, int32_t q_dtype, int32_t k, int32_t algo,
+               const int64_t* exclude_rows, float* out_scores, int64_t* out_rows, void* stream);
+
+/* K-way merge of per-shard top-K lists (the step after the NCCL all-gather): inputs are
+ * (n_lists, b, k_in) list-major -- the layout all_gather_into_tensor produces -- with row = -1
+ * padding allowed; outputs (b, k_out) best first.  out_src (may be NULL) receives for every
+ * output slot the flat source position list*k_in + j (or -1), so that callers can carry
+ * payload (rerank features) through the merge. */
+int mmr_merge_topk(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in,
+                   int32_t k_out, float* out_scores, int64_t* out_rows, int32_t* out_src,
+                   int32_t device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Rerank.  Replaces Reranker.rerank (Retrieval/reranker.py:240-333).
+ * Tables (built once, Reranker.__init__/_load_kg :29-129): per record `label_words` uint64
+ * words of label bits (get_record_label_set :161-179) and a d_kg fp32 KG vector
+ * (get_record_kg_vec :181-220; rows already L2-normalised on the host exactly as :120 does).
+ * Record index -1 = unknown record: empty label set, zero KG vector.
+ * ------------------------------------------------------------------------------------- */
+int mmr_rerank_tables_create(mmr_rerank_tables** out, const uint64_t* label_masks, int32_t label_words,
+                             const float* kg_vecs, int32_t d_kg, int64_t n_rec, int32_t device,
+                             void* stream);
+int mmr_rerank_tables_destroy(mmr_rerank_tables* tables);
+
+/* Raw feature scores of b x k candidates (reranker.py:298-319), fp64 out (b, k, 3):
+ *   [0] cosine(q_emb, cand_emb)  -- safe_cos :135-142 (0 when a norm is 0), fp32 arithmetic
+ *   [1] Jaccard(labels(q), labels(c)) -- jaccard_sets :145-149 (0 when both empty)
+ *   [2] cosine(kg(q), kg(c))
+ * q_emb: (b, d) fp32.  Candidate embeddings: `cand_emb` (b, k, d) fp32, or NULL to gather them
+ * from `index` by GLOBAL row id `cand_rows` (rows outside the shard contribute cosine 0 and are
+ * flagged in `owned` (b,k) uint8, may be NULL -- used for the sharded path).
+ * q_rec (b) / cand_rec (b, k): record indices into the tables (-1 = unknown).
+ * cand_count (b, may be NULL = k everywhere): valid candidates per query. */
+int mmr_rerank_features(const mmr_index* index, const mmr_rerank_tables* tables, const float* q_emb,
+                        const float* cand_emb, const int64_t* cand_rows, const int64_t* q_rec,
+                        const int64_t* cand_rec, const int32_t* cand_count, int32_t b, int32_t k,
+                        int32_t d, double* out_raw, uint8_t* owned, void* stream);
+/* min-max scale each feature over the query's candidates in fp64 (minmax_scale_list :152-159,
+ * all-zeros when max == min), final = alpha*emb_n + beta*lab_n + gamma*kg_n (:325), order by final
+ * descending then candidate position ascending (:327), keep topk (0 = all).  out_order (b, topk)
+ * candidate positions (-1 pad), out_scores (b, topk, 4) = final, emb_n, lab_n, kg_n. */
+int mmr_rerank_combine(const double* raw, const int32_t* cand_count, int32_t b, int32_t k, double alpha,
+                       double beta, double gamma, int32_t topk, int32_t* out_order, double* out_scores,
+                       int32_t device, void* stream);
+/* features + combine in one call (single-shard path). */
+int mmr_rerank(const mmr_index* index, const mmr_rerank_tables* tables, const float* q_emb,
+               const float* cand_emb, const int64_t* cand_rows, const int64_t* q_rec,
+               const int64_t* cand_rec, const int32_t* cand_count, int32_t b, int32_t k, int32_t d,
+               double alpha, double beta, double gamma, int32_t topk, int32_t* out_order,
+               double* out_scores, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Metrics.  Replaces Helpers/retrieval_metrics.py (precision_at_k :4-11, recall_at_k :74-79,
+ * average_precision :24-38, the reciprocal rank of mean_reciprocal_rank :56-72, ndcg_at_k :81-89),
+ * called per query by Evaluate/retrieval_eval.py:147-160.
+ * retrieved: (q, k_ret) int64 item ids (-1 = padding past ret_count); ret_count (q, may be NULL).
+ * Relevance: CSR -- rel_indptr (q+1), rel_sorted = per query sorted UNIQUE item ids;
+ * rel_list_len (q, may be NULL = unique count) = len(relevant) AS PASSED (AP denominator, a JSON
+ * list keeps duplicates).  k >= 1.  log2_tbl[i] = log2(i + 2) for i < max(k, 1) computed by the
+ * host's libm so nDCG is bit-identical to numpy's.  out: (q, 5) fp64 =
+ * [P@k, Recall@k, AP@k, RR (whole list), nDCG@k]; the mean over queries stays with the caller
+ * (np.mean's pairwise summation). */
+int mmr_metrics(const int64_t* retrieved, const int32_t* ret_count, int32_t q, int32_t k_ret,
+                const int64_t* rel_indptr, const int64_t* rel_sorted, const int64_t* rel_list_len,
+                int32_t k, const double* log2_tbl, double* out, int32_t device, void* stream);
+
+/* Label-overlap relevance + full-ranking metrics on 64-bit label masks ("next" rows:
+ * Helpers/contructGT.py:68-81 and Evaluate/retrieval_overlap.py:84-115).
+ * out_relevant (nq, ng) uint8 = ((qmask & gmask) != 0) and not (exclude_self and i == j). */
+int mmr_label_relevance(const uint64_t* q_masks, int64_t nq, const uint64_t* g_masks, int64_t ng,
+                        int32_t label_words, int32_t exclude_self, uint8_t* out_relevant,
+                        int32_t device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMR_B200_H */

@@ -1,0 +1,105 @@
+// Internal (non-ABI) declarations shared by the translation units of libmmr_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mmr {
+
+// Grow-only device buffer owned by a handle (never shrinks; freed with the handle).
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+bool is_device_ptr(const void* p);
+int elem_size(int dtype);
+
+// RAII device guard
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev);
+  ~DeviceGuard();
+};
+
+// Stages a possibly-host input on the device (async copy on `stream`) using `buf`.
+int stage_in(const void* src, size_t bytes, DeviceBuf& buf, cudaStream_t stream, const void** dev_out);
+
+// ------------------------------------------------------------------------------------------
+// kernel launchers (one per .cu)
+// ------------------------------------------------------------------------------------------
+
+// ingest.cu: rows (n, d) of dtype_in -> (n, d_pad) of dtype_store zero-padded + fp32 inverse norms.
+// src/dst are device pointers.  dst may be nullptr (norms only; src already in storage layout).
+int launch_ingest(const void* src, int dtype_in, int64_t n, int d, int64_t src_ld, void* dst,
+                  int dtype_store, int d_pad, float* inv_norm, cudaStream_t stream);
+// ingest.cu: gather rows by global id -> fp32 (m, d); outside [row_offset, row_offset+n) -> zeros.
+int launch_gather_rows(const void* emb, int dtype_store, int64_t n, int d, int d_pad, int64_t row_offset,
+                       const int64_t* rows, int64_t m, float* out, cudaStream_t stream);
+
+// scan_topk.cu: HBM-streaming scan.  q_f32 (b, d_pad) fp32 raw queries, q_inv (b) inverse norms.
+// Writes per-(query, CTA) sorted partial lists of kp = `*kp_out` keys into `partial`
+// ((b, n_parts, kp) uint64, padding key 0).  n_parts/kp are returned for the select step.
+struct ScanPlan {
+  int n_parts;   // CTAs along the gallery
+  int kp;        // keys per partial list (>= k)
+  int warps;     // warps per CTA
+  int qb;        // queries per CTA pass
+  size_t smem;   // dynamic shared memory per CTA
+  size_t partial_bytes;
+};
+int plan_scan(int64_t n, int d_pad, int dtype_store, int b, int k, int num_sms, ScanPlan* plan);
+int launch_scan(const void* emb, int dtype_store, const float* inv_norm, int64_t n, int d_pad,
+                const float* q_f32, const float* q_inv, int b, int k, const int64_t* exclude_local,
+                const ScanPlan& plan, uint64_t* partial, cudaStream_t stream);
+
+// select.cu: per query, top `k_out` of `n_parts * kp` keys -> (score, global row), best first.
+int launch_select_keys(const uint64_t* keys, int b, int64_t keys_per_query, int k_out, int64_t row_offset,
+                       float* out_scores, int64_t* out_rows, cudaStream_t stream);
+// select.cu: merge (n_lists, b, k_in) (score,row) lists -> (b, k_out); out_src optional.
+int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in, int k_out,
+                       float* out_scores, int64_t* out_rows, int32_t* out_src, cudaStream_t stream);
+
+// gemm_topk.cu: tcgen05 GEMM + fused top-K (bf16 storage).
+struct GemmPlan {
+  int n_parts;          // partial lists per query
+  int cap;              // candidate capacity per (query, part)
+  size_t cand_bytes;    // candidate buffer bytes
+  size_t count_bytes;   // per-(query, part) counts
+  int m_tiles, ctas_per_mtile;
+};
+int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan);
+int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int d_pad, const void* q_bf16,
+                     const float* q_inv, int b, int k, const int64_t* exclude_local, const GemmPlan& plan,
+                     uint64_t* cand, int32_t* counts, cudaStream_t stream);
+int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int k_out,
+                      int64_t row_offset, float* out_scores, int64_t* out_rows, cudaStream_t stream);
+
+// rerank.cu
+int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pad, int64_t row_offset,
+                           const uint64_t* label_masks, int label_words, const float* kg, int d_kg,
+                           int64_t n_rec, const float* q_emb, const float* cand_emb,
+                           const int64_t* cand_rows, const int64_t* q_rec, const int64_t* cand_rec,
+                           const int32_t* cand_count, int b, int k, int d, double* out_raw, uint8_t* owned,
+                           cudaStream_t stream);
+int launch_rerank_combine(const double* raw, const int32_t* cand_count, int b, int k, double alpha,
+                          double beta, double gamma, int topk, int32_t* out_order, double* out_scores,
+                          cudaStream_t stream);
+
+// metrics.cu
+int launch_metrics(const int64_t* retrieved, const int32_t* ret_count, int q, int k_ret,
+                   const int64_t* rel_indptr, const int64_t* rel_sorted, const int64_t* rel_list_len, int k,
+                   const double* log2_tbl, double* out, cudaStream_t stream);
+int launch_label_relevance(const uint64_t* q_masks, int64_t nq, const uint64_t* g_masks, int64_t ng,
+                           int label_words, int exclude_self, uint8_t* out, cudaStream_t stream);
+
+}  // namespace mmr

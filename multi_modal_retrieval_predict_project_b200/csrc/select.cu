@@ -1,0 +1,145 @@
+// K4: on-device K-way merge / final selection.
+//
+// Replaces the tail of np.argsort(row)[::-1][:k] (reference Evaluate/retrieval_overlap.py:90) and
+// heapq.nsmallest(K, heap) (Retrieval/retrieval.py:240): given per-(query, partition) candidate
+// lists (from the scan CTAs, the GEMM CTAs, or the per-GPU lists after the NCCL all-gather) produce
+// the global top-K per query, best first, ordered by (score desc, row asc).
+//
+// One CTA per query; candidates are packed 64-bit keys sorted with a shared-memory bitonic network.
+// More candidates than fit (8192 keys) are consumed in rounds that keep the running top-K.
+// Latency/launch-bound, tiny next to the search kernels (reported as time only).
+#include "internal.h"
+
+namespace mmr {
+namespace {
+
+constexpr int kMaxSortKeys = 8192;  // 64 KiB of shared memory
+
+struct KeySourceFlat {  // keys contiguous per query
+  const uint64_t* keys;
+  int64_t per_query;
+  __device__ __forceinline__ int64_t count(int) const { return per_query; }
+  __device__ __forceinline__ uint64_t get(int q, int64_t i) const { return keys[q * per_query + i]; }
+};
+
+struct KeySourceVar {  // (b, n_parts, cap) with per-(query, part) counts
+  const uint64_t* cand;
+  const int32_t* counts;
+  int n_parts;
+  int cap;
+  __device__ __forceinline__ int64_t count(int) const { return static_cast<int64_t>(n_parts) * cap; }
+  __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
+    const int part = static_cast<int>(i / cap);
+    const int j = static_cast<int>(i - static_cast<int64_t>(part) * cap);
+    const int c = counts[static_cast<int64_t>(q) * n_parts + part];
+    return j < (c < cap ? c : cap) ? cand[(static_cast<int64_t>(q) * n_parts + part) * cap + j] : 0ull;
+  }
+};
+
+struct KeySourceLists {  // (n_lists, b, k_in) score/row pairs with GLOBAL rows
+  const float* scores;
+  const int64_t* rows;
+  int n_lists, b, k_in;
+  __device__ __forceinline__ int64_t count(int) const { return static_cast<int64_t>(n_lists) * k_in; }
+  __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
+    const int l = static_cast<int>(i / k_in);
+    const int j = static_cast<int>(i - static_cast<int64_t>(l) * k_in);
+    const int64_t at = (static_cast<int64_t>(l) * b + q) * k_in + j;
+    const int64_t r = rows[at];
+    return r < 0 ? 0ull : make_key(scores[at], static_cast<uint32_t>(r));
+  }
+};
+
+template <typename Source>
+__global__ void __launch_bounds__(1024, 1)
+select_topk_kernel(Source src, int k_out, int sz, int keep, int64_t row_offset, float* __restrict__ out_scores,
+                   int64_t* __restrict__ out_rows, int32_t* __restrict__ out_src) {
+  extern __shared__ __align__(16) uint64_t s[];
+  const int q = blockIdx.x;
+  const int64_t total = src.count(q);
+  int64_t pos = 0;
+  bool first = true;
+  do {
+    const int base = first ? 0 : keep;
+    const int64_t room = sz - base;
+    const int64_t chunk = (total - pos) < room ? (total - pos) : room;
+    for (int i = threadIdx.x; i < sz - base; i += blockDim.x) {
+      s[base + i] = (i < chunk) ? src.get(q, pos + i) : 0ull;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(s, sz);
+    pos += chunk;
+    first = false;
+  } while (pos < total);
+
+  for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+    const uint64_t key = (i < sz) ? s[i] : 0ull;
+    const int64_t o = static_cast<int64_t>(q) * k_out + i;
+    if (key == 0ull) {
+      out_scores[o] = -INFINITY;
+      out_rows[o] = -1;
+      if (out_src != nullptr) out_src[o] = -1;
+    } else {
+      out_scores[o] = key_score(key);
+      out_rows[o] = row_offset + static_cast<int64_t>(key_row(key));
+      if (out_src != nullptr) {
+        int found = -1;
+        for (int64_t j = 0; j < total; ++j) {
+          if (src.get(q, j) == key) {
+            found = static_cast<int>(j);
+            break;
+          }
+        }
+        out_src[o] = found;
+      }
+    }
+  }
+}
+
+template <typename Source>
+int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_offset, float* out_scores,
+                  int64_t* out_rows, int32_t* out_src, cudaStream_t stream) {
+  if (b == 0 || k_out == 0) return MMR_OK;
+  const int keep = next_pow2(k_out);
+  int sz;
+  if (per_query <= kMaxSortKeys) {
+    sz = next_pow2(static_cast<int>(per_query < 2 ? 2 : per_query));
+    if (sz < keep) sz = keep;
+  } else {
+    sz = kMaxSortKeys;
+    if (keep * 2 > sz) return fail(MMR_EUNSUP, "select: k too large for the merge kernel");
+  }
+  if (sz < 2) sz = 2;
+  int threads = sz / 2;
+  threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
+  const size_t smem = static_cast<size_t>(sz) * sizeof(uint64_t);
+  auto kern = select_topk_kernel<Source>;
+  MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<b, threads, smem, stream>>>(src, k_out, sz, keep, row_offset, out_scores, out_rows, out_src);
+  MMR_CUDA_TRY(cudaGetLastError());
+  return MMR_OK;
+}
+
+}  // namespace
+
+int launch_select_keys(const uint64_t* keys, int b, int64_t keys_per_query, int k_out, int64_t row_offset,
+                       float* out_scores, int64_t* out_rows, cudaStream_t stream) {
+  KeySourceFlat src{keys, keys_per_query};
+  return launch_select(src, b, keys_per_query, k_out, row_offset, out_scores, out_rows, nullptr, stream);
+}
+
+int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int k_out,
+                      int64_t row_offset, float* out_scores, int64_t* out_rows, cudaStream_t stream) {
+  KeySourceVar src{cand, counts, n_parts, cap};
+  return launch_select(src, b, static_cast<int64_t>(n_parts) * cap, k_out, row_offset, out_scores, out_rows,
+                       nullptr, stream);
+}
+
+int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in, int k_out,
+                       float* out_scores, int64_t* out_rows, int32_t* out_src, cudaStream_t stream) {
+  KeySourceLists src{scores, rows, n_lists, b, k_in};
+  return launch_select(src, b, static_cast<int64_t>(n_lists) * k_in, k_out, 0, out_scores, out_rows, out_src,
+                       stream);
+}
+
+}  // namespace mmr

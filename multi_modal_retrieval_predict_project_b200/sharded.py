@@ -1,0 +1,83 @@
+"""Row-sharded search across the GPUs of one NVSwitch box (one process per GPU).
+
+Gallery rows are split into contiguous shards; every rank searches its own
+shard (no data-path collective), then ONE exchange: an NCCL all-gather of the per-rank top-K
+``(score fp32, global row int64)`` lists over NVLink, followed by the on-device K-way merge
+(csrc/select.cu).  ``torch.distributed`` is plumbing only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+from . import _lib
+
+
+def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row block of ``rank``: ``[rank*ceil(N/G), min(N, (rank+1)*ceil(N/G)))``."""
+    per = (n_total + world - 1) // world
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+def merge_topk(scores, rows, k_out: int, want_src: bool = False):
+    """K-way merge of ``(n_lists, B, K_in)`` CUDA tensors -> ``(B, k_out)`` best first (score desc,
+    row asc).  With ``want_src`` also returns the flat source position ``list*K_in + j`` of every
+    output slot (int32), so callers can gather payload carried next to the lists."""
+    import torch
+    assert scores.is_cuda and rows.is_cuda and scores.shape == rows.shape and scores.dim() == 3
+    scores = scores.float().contiguous()
+    rows = rows.to(torch.int64).contiguous()
+    n_lists, b, k_in = scores.shape
+    dev = scores.device.index or 0
+    out_s = torch.empty((b, k_out), dtype=torch.float32, device=scores.device)
+    out_r = torch.empty((b, k_out), dtype=torch.int64, device=scores.device)
+    src = torch.empty((b, k_out), dtype=torch.int32, device=scores.device) if want_src else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mmr_merge_topk(_lib.ptr(scores), _lib.ptr(rows), n_lists, b, k_in, k_out, _lib.ptr(out_s),
+                                      _lib.ptr(out_r), _lib.ptr(src), dev, _lib.current_stream(dev)))
+    if want_src:
+        # the kernel reports positions in (list, j) order over a (list, b, k) layout: list*k_in + j
+        return out_r, out_s, src
+    return out_r, out_s
+
+
+class ShardedSearcher:
+    """Per-rank shard + all-gather + merge.  ``engine`` holds this rank's rows (``row_offset`` set
+    to the shard's first global row).  Works with any initialised ``torch.distributed`` process
+    group whose backend supports CUDA tensors (NCCL); with world size 1 it is a pass-through."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._gs = self._gr = None
+
+    def search(self, queries, K: int, algo: Optional[str] = None):
+        import torch
+        import torch.distributed as dist
+        rows, scores = self.engine.search(queries, K, algo=algo)
+        if self.world == 1:
+            return rows, scores
+        b = rows.shape[0]
+        if self._gs is None or self._gs.shape[1:] != scores.shape:
+            self._gs = torch.empty((self.world, b, K), dtype=torch.float32, device=scores.device)
+            self._gr = torch.empty((self.world, b, K), dtype=torch.int64, device=scores.device)
+        dist.all_gather_into_tensor(self._gs, scores, group=self.group)
+        dist.all_gather_into_tensor(self._gr, rows, group=self.group)
+        return merge_topk(self._gs, self._gr, K)
+
+    def rerank(self, reranker, q_embs, rows, q_rec, cand_rec, topk: int = 0):
+        """Rerank merged global candidates: the label/KG tables are replicated, the candidate
+        embedding cosine is computed by the rank that owns the row and summed across ranks
+        (exactly one owner per candidate), then every rank combines."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return reranker.rerank_device(self.engine, q_embs, rows, q_rec, cand_rec, topk)
+        raw = reranker.features_device(self.engine, q_embs, rows, q_rec, cand_rec)
+        emb = raw[..., 0].contiguous()
+        dist.all_reduce(emb, op=dist.ReduceOp.SUM, group=self.group)
+        raw[..., 0] = emb
+        return reranker.combine_device(raw, topk)

@@ -1,0 +1,88 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mmr_b200.h declares; host-side
+logic (id interning, label bit masks, shard bounds); loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from multi_modal_retrieval_predict_project_b200 import _lib
+    from multi_modal_retrieval_predict_project_b200.build import build
+    build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from multi_modal_retrieval_predict_project_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mmr_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(mmr_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 16
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.mmr_abi_version() == int(re.search(r"#define MMR_ABI_VERSION (\d+)", hdr).group(1))
+
+
+def test_argument_errors_without_touching_the_gpu(lib):
+    from multi_modal_retrieval_predict_project_b200 import _lib
+    h = C.c_void_p()
+    assert lib.mmr_index_create(C.byref(h), None, 10, 8, 0, 0, 0, 0, 0, None) == _lib.MMR_EINVAL
+    assert b"emb is NULL" in lib.mmr_last_error()
+    assert lib.mmr_search(None, None, 1, 0, 5, 0, None, None, None, None) == _lib.MMR_EINVAL
+    assert lib.mmr_metrics(None, None, 3, 5, None, None, None, 0, None, None, 0, None) == _lib.MMR_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(_lib.MMR_EINVAL)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine
+    from multi_modal_retrieval_predict_project_b200.Helpers import precision_at_k
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200RetrievalEngine.from_arrays(np.zeros((4, 8), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        precision_at_k(["a"], ["a"], 1)
+    # and the raw ABI refuses as well
+    from multi_modal_retrieval_predict_project_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    x = np.zeros((4, 8), np.float32)
+    st = lib.mmr_index_create(C.byref(h), x.ctypes.data, 4, 8, 0, 0, 0, 0, 0, None)
+    assert st in (_lib.MMR_ENODEV, _lib.MMR_ECUDA)
+
+
+def test_metric_id_interning():
+    from multi_modal_retrieval_predict_project_b200.Helpers.retrieval_metrics import _intern
+    ret, cnt, indptr, rel, ll = _intern([["a", "b", "a"], [], ["z"]], [["b", "b", "q"], ["a"], []])
+    assert cnt.tolist() == [3, 0, 1] and ll.tolist() == [3, 1, 0]
+    assert indptr.tolist() == [0, 2, 3, 3]
+    assert ret[0, 0] == ret[0, 2] != ret[0, 1] and ret[1, 0] == -1
+    assert sorted(rel[0:2].tolist()) == rel[0:2].tolist() and ret[0, 1] in rel[0:2]
+
+
+def test_label_bit_masks_follow_int_eq_1_rule():
+    from multi_modal_retrieval_predict_project_b200.Retrieval.reranker import Reranker
+    df = pd.DataFrame({"id": ["a", "b", "c", "c"], "L0": [1, 0, 1, 1], "L1": [1.0, 1.9, np.nan, 0.0],
+                       "txt": ["x", "1", "no", "2"], "L3": [True, False, True, True]}).set_index("id")
+    r = Reranker.__new__(Reranker)
+    r.labels_df = df
+    masks, cols = r._label_bits()
+    assert cols == ["L0", "L1", "txt", "L3"]
+    assert masks[:, 0].tolist() == [0b1011, 0b0110, 0, 0]     # duplicated id "c" -> empty set
+
+
+def test_shard_bounds_cover_rows():
+    from multi_modal_retrieval_predict_project_b200.sharded import shard_bounds
+    for n, w in ((10, 3), (100_000_000, 8), (5, 8), (0, 2)):
+        b = [shard_bounds(n, w, r) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))

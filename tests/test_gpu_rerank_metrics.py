@@ -1,0 +1,178 @@
+"""GPU parity: rerank + metrics kernels (through the C ABI) vs the golden vectors and the oracle."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import gt as ogt
+from oracle import metrics as om
+from oracle import rerank as orr
+from oracle import search as osr
+from tests._fixtures import GOLDEN, assert_rerank_close, build_rerank_artifacts
+
+pytestmark = pytest.mark.gpu
+
+# fp32 cosines computed with a different summation order than numpy's, then min-max scaled
+# (amplified by 1/(max-min)): tolerance on the fp64 combined values, stated per north_star (1e-5).
+TOL = dict(rtol=1e-5, atol=5e-6)
+
+
+def test_rerank_matches_reference_golden(tmp_path):
+    from multi_modal_retrieval_predict_project_b200 import Reranker
+    a = build_rerank_artifacts(str(tmp_path))
+    for name, v in a["golden"]["variants"].items():
+        al, be, ga = v["weights"]
+        rer = Reranker(a["kg_dir"], a["csv"], al, be, ga, device=0)
+        for qi, res in enumerate(v["results"]):
+            cand = res["cand"]
+            cand_ids = [a["ids"][j] for j in cand]
+            embs = a["g"][cand]
+            r1 = rer.rerank(a["qids"][qi], cand_ids, candidate_embs=embs, query_emb=a["qs"][qi], topk=10)
+            assert_rerank_close(r1, [tuple(t) for t in res["qemb_top10"]], **TOL)
+            lookup = {cid: a["g"][j] for cid, j in zip(cand_ids, cand)}
+            lookup[a["qids"][qi]] = a["qs"][qi]
+            r2 = rer.rerank(a["qids"][qi], cand_ids, candidate_embs=embs, candidate_emb_lookup=lookup)
+            assert_rerank_close(r2, [tuple(t) for t in res["lookup_all"]], **TOL)
+            r3 = rer.rerank(cand_ids[3], cand_ids, candidate_embs=embs, topk=5)
+            assert_rerank_close(r3, [tuple(t) for t in res["gallery_qid_top5"]], **TOL)
+            r4 = rer.rerank("not-a-record", cand_ids, candidate_embs=embs, query_emb=a["qs"][qi], topk=5)
+            assert_rerank_close(r4, [tuple(t) for t in res["unknown_qid_top5"]], **TOL)
+            assert all(isinstance(x, float) for t in r1 for x in t[1:]) and isinstance(r1[0][0], str)
+        rer.close()
+
+
+def test_rerank_errors_match_reference(tmp_path):
+    from multi_modal_retrieval_predict_project_b200 import Reranker
+    a = build_rerank_artifacts(str(tmp_path))
+    rer = Reranker(a["kg_dir"], a["csv"], device=0)
+    with pytest.raises(ValueError, match="Please provide candidate_embs"):
+        rer.rerank("t0", ["g1", "g2"])
+    with pytest.raises(ValueError, match="rows must match"):
+        rer.rerank("t0", ["g1", "g2"], candidate_embs=a["g"][:3], query_emb=a["qs"][0])
+    with pytest.raises(ValueError, match="Query embedding not found"):
+        rer.rerank("t0", ["g1", "g2"], candidate_embs=a["g"][:2])
+    with pytest.raises(FileNotFoundError):
+        Reranker(str(tmp_path / "missing"), a["csv"], device=0)
+    # label sets / kg vectors agree with the oracle's python-loop versions
+    ora = orr.OracleReranker(a["kg_dir"], a["csv"])
+    for rid in ["g0", "g5", "g6", "g13", "t2", "t3", "zzz"]:
+        assert rer.get_record_label_set(rid) == ora.get_record_label_set(rid)
+        assert np.allclose(rer.get_record_kg_vec(rid), ora.get_record_kg_vec(rid), atol=1e-6)
+
+
+def test_engine_retrieve_with_reranker_vs_oracle(tmp_path):
+    """retrieve(q, K, reranker=..., query_id=..., rerank_topk=...) (reference retrieval.py:246-269):
+    exact candidates -> rerank; the stored gallery row replaces q when query_id is a gallery id."""
+    from multi_modal_retrieval_predict_project_b200 import Reranker, make_retrieval_engine
+    a = build_rerank_artifacts(str(tmp_path))
+    eng = make_retrieval_engine(a["features_path"], a["ids_path"], method="b200")
+    rer = Reranker(a["kg_dir"], a["csv"], device=0)
+    ora = orr.OracleReranker(a["kg_dir"], a["csv"])
+    for qi in range(len(a["qids"])):
+        for qid, qvec in ((a["qids"][qi], a["qs"][qi]), (a["ids"][qi], a["qs"][qi])):
+            ids, scores = eng.retrieve(qvec, K=10, reranker=rer, query_id=qid, rerank_topk=5, seed=1)
+            wr, _ = osr.exact_topk(qvec[None], a["g"], 10)
+            cand_ids = [a["ids"][int(j)] for j in wr[0]]
+            q_emb = a["g"][a["ids"].index(qid)] if qid in a["ids"] else qvec
+            want = ora.rerank(qid, cand_ids, candidate_embs=a["g"][wr[0]], query_emb=q_emb, topk=5)
+            got = list(zip(ids, scores))
+            assert len(got) == 5
+            assert_rerank_close([(i, s, 0, 0, 0) for i, s in got], [(t[0], t[1], 0, 0, 0) for t in want], **TOL)
+    # a foreign reranker object with the reference interface works too (here: the oracle)
+    ids, scores = eng.retrieve(a["qs"][0], K=10, reranker=ora, query_id=a["qids"][0])
+    ids2, scores2 = eng.retrieve(a["qs"][0], K=10, reranker=rer, query_id=a["qids"][0])
+    assert_rerank_close([(i, s, 0, 0, 0) for i, s in zip(ids2, scores2)],
+                        [(i, s, 0, 0, 0) for i, s in zip(ids, scores)], **TOL)
+
+
+def test_batched_device_rerank_vs_oracle():
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, synth
+    n, d, b, k = 5000, 256, 40, 100
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=5, clustered=True))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=6, clustered=True))
+    rng = np.random.default_rng(7)
+    bits = (rng.random((n + b, 43)) < 0.1)
+    masks = (bits.astype(np.uint64) << np.arange(43, dtype=np.uint64)).sum(axis=1).astype(np.uint64)
+    kg = rng.standard_normal((n + b, 300)).astype(np.float32)
+    kg = kg / (np.linalg.norm(kg, axis=1, keepdims=True) + 1e-12)
+    eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
+    rer = Reranker.from_tables(masks, kg, alpha=0.4, beta=0.2, gamma=0.2, device=0)
+    qd = torch.from_numpy(q).cuda()
+    rows, _ = eng.search(qd, k)
+    order, sc = rer.rerank_device(eng, qd, rows, torch.arange(n, n + b, device="cuda"), rows.clone(), topk=20)
+    order, sc, rows = order.cpu().numpy(), sc.cpu().numpy(), rows.cpu().numpy()
+    for i in range(b):
+        cand = rows[i]
+        emb = [orr.safe_cos(q[i], g[j]) for j in cand]
+        lab = [orr.jaccard_sets(set(np.nonzero(bits[n + i])[0]), set(np.nonzero(bits[j])[0])) for j in cand]
+        kgs = [orr.safe_cos(kg[n + i], kg[j]) for j in cand]
+        e, l, kk_ = (np.array(orr.minmax_scale_list(x)) for x in (emb, lab, kgs))
+        final = 0.4 * e + 0.2 * l + 0.2 * kk_
+        want = np.lexsort((np.arange(k), -final))[:20]
+        got_final = sc[i, :, 0]
+        assert np.allclose(got_final, final[want], **TOL), i
+        assert np.allclose(sc[i, :, 2], l[order[i]], rtol=0, atol=0)          # Jaccard is exact
+        mism = order[i] != want
+        assert np.all(np.abs(final[order[i]][mism] - final[want][mism]) < 1e-5)
+
+
+def test_metrics_match_reference_golden_bit_for_bit():
+    from multi_modal_retrieval_predict_project_b200.Helpers import retrieval_metrics as m
+    gold = json.load(open(GOLDEN / "metrics.json"))
+    for c in gold["cases"]:
+        ret, rel = c["retrieved"], c["relevant"]
+        for k_s, w in c["by_k"].items():
+            k = int(k_s)
+            t = m.per_query_metrics([ret], [rel], k)[0]
+            assert (t[0], t[1], t[2], t[4]) == (w["p"], w["r"], w["ap_list"], w["ndcg"]), (ret, rel, k)
+            assert m.average_precision(ret, set(rel), k) == w["ap_set"]
+        assert m.average_precision(ret, rel, None) == c["ap_none"]
+        assert m.mean_reciprocal_rank([ret], [rel]) == c["rr"]
+    rets = [c["retrieved"] for c in gold["cases"]]; rels = [c["relevant"] for c in gold["cases"]]
+    for k_s, w in gold["agg"].items():
+        k = int(k_s)
+        assert float(np.mean([m.precision_at_k(r, l, k=k) for r, l in zip(rets[:5], rels[:5])])) == \
+            float(np.mean([om.precision_at_k(r, l, k) for r, l in zip(rets[:5], rels[:5])]))
+        assert m.mean_average_precision(rets, rels, k=k) == w["mAP"]
+        assert m.mean_reciprocal_rank(rets, rels) == w["MRR"]
+        e = m.evaluate_retrieval(rets, rels, k)
+        assert (e["P"], e["R"], e["mAP"], e["MRR"], e["nDCG"]) == (w["P"], w["R"], w["mAP"], w["MRR"], w["nDCG"])
+    with pytest.raises(ZeroDivisionError):
+        m.precision_at_k(["a"], ["a"], k=0)
+
+
+def test_metrics_large_vs_oracle_identical():
+    """cfg1-style: 1500 queries, top-10 lists, ~1800 relevant ids each -- values identical."""
+    from multi_modal_retrieval_predict_project_b200.Helpers import per_query_metrics
+    rng = np.random.default_rng(17)
+    universe = [f"g{i}" for i in range(7500)]
+    rets, rels = [], []
+    for i in range(1500):
+        rets.append([universe[j] for j in rng.integers(0, 7500, size=10)])
+        rels.append([universe[j] for j in rng.choice(7500, size=int(rng.integers(0, 3000)), replace=False)])
+    for k in (5, 10):
+        got = per_query_metrics(rets, rels, k)
+        want = om.per_query_table(rets, rels, k)
+        assert np.array_equal(got, want)
+
+
+def test_label_relevance_matches_reference_gt():
+    import torch
+    from multi_modal_retrieval_predict_project_b200.Evaluate import label_masks, relevance_lists
+    gold = json.load(open(GOLDEN / "gt.json"))
+    z = np.load(GOLDEN / "gt_inputs.npz")
+    te_ids = [f"te{i}" for i in range(z["test_labels"].shape[0])]
+    tr_ids = [f"tr{i}" for i in range(z["train_labels"].shape[0])]
+    assert relevance_lists(z["test_labels"], te_ids, z["test_labels"], te_ids, exclude_self=True) == gold["test_relevance"]
+    assert relevance_lists(z["test_labels"], te_ids, z["train_labels"], tr_ids, exclude_self=False) == gold["test_to_train"]
+
+
+def test_compute_ranking_metrics_matches_reference():
+    from multi_modal_retrieval_predict_project_b200.Evaluate import compute_ranking_metrics
+    gold = json.load(open(GOLDEN / "gt.json"))
+    z = np.load(GOLDEN / "gt_inputs.npz")
+    for k_s, w in gold["ranking"].items():
+        mrr, hit, rec = compute_ranking_metrics(z["queries"], z["gallery"], z["test_labels"], z["train_labels"],
+                                                k=int(k_s))
+        assert np.isclose(mrr, w[0], rtol=1e-9) and hit == w[1] and np.isclose(rec, w[2], rtol=1e-9)

@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA search path (through the C ABI) vs the oracle and the golden vectors."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import search as osr
+from tests._fixtures import load_search_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(g, **kw):
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine
+    return B200RetrievalEngine.from_arrays(g, device=0, **kw)
+
+
+def _check(rows, scores, want_rows, want_scores, rtol, atol=1e-7):
+    assert rows.shape == want_rows.shape
+    for i in range(rows.shape[0]):
+        ok, why = osr.topk_matches(rows[i], scores[i], want_rows[i], want_scores[i], rtol=rtol, atol=atol)
+        assert ok, (i, why)
+
+
+@pytest.mark.parametrize("name", ["gauss", "clustered"])
+def test_fp32_search_matches_reference_golden(name):
+    """ids bit-exact except exact-score ties, scores within 1e-5 relative (north_star)."""
+    c = load_search_case(name)
+    eng = _engine(c["gallery"])
+    k = c["order_top"].shape[1]
+    rows, scores = eng.search(c["queries"], k)
+    want_rows = c["order_top"].astype(np.int64)
+    want_scores = np.take_along_axis(c["sim"], want_rows, axis=1)
+    _check(rows, scores, want_rows, want_scores, rtol=1e-5)
+    # zero query (row 1) scores exactly 0 everywhere; the zero gallery row (7) scores exactly 0
+    assert np.all(scores[1] == 0.0)
+    # exact duplicates (rows 3, 11, 12) must come out in ascending row order when they tie
+    for i in range(rows.shape[0]):
+        pos = {int(r): j for j, r in enumerate(rows[i])}
+        if all(r in pos for r in (3, 11, 12)):
+            assert pos[3] < pos[11] < pos[12]
+
+
+def test_fp32_cfg1_openi_scale_vs_oracle():
+    """BASELINE cfg1: 7.5k x 1024 fp32 gallery, 1.5k queries, top-10 (parity case)."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = synth.make_embeddings(7500, 1024, seed=synth.SEED)
+    q = synth.make_embeddings(1500, 1024, seed=synth.SEED + 1)
+    want_rows, want_scores = osr.exact_topk(q, g, 10)
+    eng = _engine(g)
+    rows, scores = eng.search(q, 10)
+    _check(rows, scores, want_rows, want_scores, rtol=1e-5)
+    assert (rows == want_rows).mean() > 0.999
+
+
+@pytest.mark.parametrize("algo", ["scan", "gemm"])
+@pytest.mark.parametrize("b,k", [(1, 10), (3, 100), (8, 7), (64, 100), (200, 10)])
+def test_bf16_search_vs_oracle(algo, b, k):
+    """bf16 storage: the oracle consumes the SAME bf16-rounded values upcast to fp32."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    n, d = 30000, 512
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=11))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=12))
+    eng = _engine(g, dtype="bfloat16")
+    rows, scores = eng.search(q, k, algo=algo)
+    want_rows, want_scores = osr.exact_topk(q, g, k)
+    _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+    # exact recall@K against the fp64 ranking, epsilon rule at the K boundary
+    r64, s64 = osr.exact_topk_f64(q, g, k)
+    for i in range(b):
+        missing = set(r64[i].tolist()) - set(rows[i].tolist())
+        for m in missing:
+            j = int(np.nonzero(r64[i] == m)[0][0])
+            assert s64[i, j] - s64[i, -1] <= 1e-5, (i, m)
+
+
+@pytest.mark.parametrize("algo", ["scan", "gemm"])
+def test_unrounded_queries_are_rounded_to_bf16(algo):
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = synth.make_embeddings(5000, 256, seed=21)
+    q = synth.make_embeddings(20, 256, seed=22)
+    eng = _engine(g, dtype="bfloat16")
+    rows, scores = eng.search(q, 10, algo=algo)
+    want_rows, want_scores = osr.exact_topk(osr.to_bf16_round(q), osr.to_bf16_round(g), 10)
+    _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+@pytest.mark.parametrize("n,d,b,k", [(1, 64, 1, 5), (7, 96, 3, 10), (100, 100, 5, 100), (513, 40, 2, 1),
+                                     (1000, 1024, 4, 17), (300, 130, 33, 300)])
+def test_edge_shapes(dtype, n, d, b, k):
+    """K > N (tail is -1/-inf), D not a multiple of 64, tiny galleries, ragged batch sizes."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = synth.make_embeddings(n, d, seed=31)
+    q = synth.make_embeddings(b, d, seed=32)
+    if dtype == "bfloat16":
+        g, q = osr.to_bf16_round(g), osr.to_bf16_round(q)
+    eng = _engine(g, dtype=dtype)
+    rows, scores = eng.search(q, k)
+    kk = min(k, n)
+    want_rows, want_scores = osr.exact_topk(q, g, k)
+    _check(rows[:, :kk], scores[:, :kk], want_rows, want_scores, rtol=2e-5, atol=1e-6)
+    assert np.all(rows[:, kk:] == -1) and np.all(np.isneginf(scores[:, kk:]))
+
+
+def test_exclude_rows_and_row_offset():
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = synth.make_embeddings(2000, 128, seed=41)
+    eng = _engine(g, row_offset=5000)
+    q = g[:50]
+    rows, scores = eng.search(q, 5)
+    assert np.array_equal(rows[:, 0], np.arange(50) + 5000)          # self match first
+    rows2, scores2 = eng.search(q, 5, exclude_rows=np.arange(50) + 5000)
+    assert not np.any(rows2 == (np.arange(50) + 5000)[:, None])
+    assert np.array_equal(rows2[:, :4], rows[:, 1:])                  # rest shifts up by one
+    # link graph == oracle link graph (Retrieval/retrieval.py:121-138 form)
+    eng0 = _engine(g[:400])
+    graph = eng0.build_link_graph(threshold=0.05, max_links=6)
+    want = osr.build_link_graph(g[:400], 0.05, 6)
+    sim = osr.cosine_similarity(g[:400])
+    for i, (a, b_) in enumerate(zip(graph, want)):
+        if a != b_:
+            assert len(a) == len(b_) and np.allclose(sim[i, a], sim[i, b_], atol=2e-6), (i, a, b_)
+
+
+def test_retrieve_signature_and_types(tmp_path):
+    """The reference contract: retrieve(q (D,)|(1,D), K) -> (List[str], List[float]) best first."""
+    from multi_modal_retrieval_predict_project_b200 import make_retrieval_engine, synth
+    g = synth.make_embeddings(300, 64, seed=51)
+    ids = synth.make_ids(300, "rec")
+    fp, ip = synth.write_gallery(str(tmp_path), "train", g, ids)
+    eng = make_retrieval_engine(fp, ip, method="DLS", link_threshold=0.3, max_links=8)   # kwargs ignored
+    want_rows, want_scores = osr.exact_topk(g[5:6] * 2.0, g, 5)
+    for q in (g[5] * 2.0, (g[5] * 2.0).reshape(1, -1), (g[5] * 2.0).astype(np.float64)):
+        out_ids, out_scores = eng.retrieve(q, K=5, seed_size=5, max_steps=100, seed=2709)
+        assert isinstance(out_ids, list) and isinstance(out_scores, list)
+        assert all(isinstance(x, str) for x in out_ids) and all(isinstance(x, float) for x in out_scores)
+        assert out_ids == [ids[int(r)] for r in want_rows[0]] and out_ids[0] == "rec5"
+        assert np.allclose(out_scores, want_scores[0], rtol=1e-5)
+    nested_ids, nested_scores = eng.retrieve(g[:3], K=4)
+    assert len(nested_ids) == 3 and [x[0] for x in nested_ids] == ["rec0", "rec1", "rec2"]
+    assert eng.retrieve(g[0], K=1000)[0].__len__() == 300                      # K > N -> N results
+    assert np.array_equal(eng.get_embeddings_for_ids(["rec3", "nope"]), np.vstack([g[3], np.zeros(64, np.float32)]))
+    with pytest.raises(ValueError, match="Unknown retrieval method"):
+        make_retrieval_engine(fp, ip, method="faiss")
+    with pytest.raises(ValueError):
+        eng.search(np.zeros((1, 65), np.float32), 3)
+
+
+def test_device_tensors_in_and_out_and_c_abi_direct():
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import _lib, synth
+    g = osr.to_bf16_round(synth.make_embeddings(10000, 512, seed=61))
+    q = osr.to_bf16_round(synth.make_embeddings(4, 512, seed=62))
+    gd = torch.from_numpy(g).cuda().to(torch.bfloat16)
+    eng = _engine(gd, dtype="bfloat16", borrow=True, keep_host=False)
+    rows, scores = eng.search(torch.from_numpy(q).cuda(), 10)
+    assert rows.is_cuda and scores.is_cuda
+    want_rows, want_scores = osr.exact_topk(q, g, 10)
+    _check(rows.cpu().numpy(), scores.cpu().numpy(), want_rows, want_scores, rtol=2e-5, atol=1e-6)
+    # virtual ids + device gather
+    assert eng.retrieve(q[0], K=3)[0] == [f"g{int(r)}" for r in want_rows[0][:3]]
+    assert np.array_equal(eng.get_embeddings_for_ids(["g7", "zzz"]), np.vstack([g[7], np.zeros(512, np.float32)]))
+    # raw C ABI with host buffers
+    lib = _lib.load()
+    out_s = np.empty((4, 10), np.float32); out_r = np.empty((4, 10), np.int64)
+    st = lib.mmr_search(eng._handle, q.ctypes.data, 4, _lib.MMR_F32, 10, _lib.ALGO_SCAN, None,
+                        out_s.ctypes.data, out_r.ctypes.data, None)
+    assert st == 0, lib.mmr_last_error()
+    _check(out_r, out_s, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+    assert lib.mmr_search(eng._handle, q.ctypes.data, 4, _lib.MMR_F32, 0, 0, None, out_s.ctypes.data,
+                          out_r.ctypes.data, None) == _lib.MMR_EINVAL
+    assert b"k >= 1" in lib.mmr_last_error()
+
+
+@pytest.mark.parametrize("algo", ["scan", "gemm"])
+def test_merge_topk_matches_single_shard(algo):
+    """Row shards + K-way merge == one index (the multi-GPU data path, emulated on one device)."""
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import _lib, synth
+    from multi_modal_retrieval_predict_project_b200.sharded import merge_topk
+    g = osr.to_bf16_round(synth.make_embeddings(9001, 256, seed=71))
+    q = osr.to_bf16_round(synth.make_embeddings(37, 256, seed=72))
+    full = _engine(g, dtype="bfloat16")
+    rows, scores = full.search(q, 50, algo=algo)
+    bounds = [0, 2500, 2500 + 3000, 9001]
+    parts_r, parts_s = [], []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        e = _engine(g[lo:hi], dtype="bfloat16", row_offset=lo)
+        r, s = e.search(torch.from_numpy(q).cuda(), 50, algo=algo)
+        parts_r.append(r); parts_s.append(s)
+    mr, ms, src = merge_topk(torch.stack(parts_s), torch.stack(parts_r), 50, want_src=True)
+    assert np.array_equal(mr.cpu().numpy(), rows) and np.array_equal(ms.cpu().numpy(), scores)
+    flat_r = torch.stack(parts_r).permute(1, 0, 2).reshape(37, -1)
+    assert torch.equal(torch.gather(flat_r, 1, src.long()), mr)
