@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import abc
 import json
+import os
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -217,7 +218,10 @@ class B200RetrievalEngine(RetrievalEngine):
         K = int(K)
         if K < 1:
             raise ValueError("K must be >= 1")
-        a = _lib.ALGOS[algo if algo is not None else self.algo]
+        name = algo if algo is not None else self.algo
+        if name == "auto":  # debugging aid: MMR_B200_ALGO=scan|gemm overrides the automatic choice
+            name = os.environ.get("MMR_B200_ALGO", "auto")
+        a = _lib.ALGOS[name]
         on_device = _is_tensor(queries) and queries.is_cuda
         if _is_tensor(queries):
             q = queries.detach()

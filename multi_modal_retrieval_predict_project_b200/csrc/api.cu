@@ -399,13 +399,14 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
 
   if (use == MMR_ALGO_GEMM) {
     GemmPlan gp;
-    MMR_TRY(plan_gemm(ix->n, ix->d_pad, b, k, ix->num_sms, &gp));
+    const int k_eff = k + (d_excl != nullptr ? 1 : 0);  // the excluded row is dropped by the select step
+    MMR_TRY(plan_gemm(ix->n, ix->d_pad, b, k_eff, ix->num_sms, &gp));
     MMR_TRY(ix->partial.ensure(gp.cand_bytes));
     MMR_TRY(ix->counts.ensure(gp.count_bytes));
-    MMR_TRY(launch_gemm_topk(ix->emb, ix->inv_norm, ix->n, ix->d_pad, ix->q_store.p, ix->q_inv.as<float>(), b, k,
+    MMR_TRY(launch_gemm_topk(ix->emb, ix->inv_norm, ix->n, ix->d_pad, ix->q_store.p, ix->q_inv.as<float>(), b, k_eff,
                              d_excl, gp, ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), stream));
-    MMR_TRY(launch_select_var(ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), b, gp.n_parts, gp.cap, k,
-                              ix->row_offset, d_scores, d_rows, stream));
+    MMR_TRY(launch_select_var(ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), b, gp.n_parts, gp.cap, k_eff, k,
+                              ix->row_offset, d_excl, d_scores, d_rows, stream));
   } else {
     const float* q_f32 = nullptr;
     if (ix->dtype == MMR_F32) {

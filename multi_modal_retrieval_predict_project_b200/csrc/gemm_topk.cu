@@ -1,7 +1,525 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// K1 + K3: tcgen05 / TMEM bf16 GEMM with a fused inverse-norm scale + top-K epilogue.
+//
+// Replaces cosine_similarity(Q, G) + np.argsort(row)[::-1][:k] for a BATCH of queries (reference
+// Evaluate/retrieval_overlap.py:85,90; Retrieval/retrieval.py:128,134): the (Q, N) score matrix is
+// never written to HBM.
+//
+//   scores[m, n] = sum_d Q[m, d] * G[n, d]      Q: (b, d_pad) bf16, G: (n, d_pad) bf16, both K-major
+//
+// CTA = (query tile of 128 rows) x (contiguous range of gallery tiles of 256 rows).  Warp roles:
+//   warp 0   TMA producer: cp.async.bulk.tensor 128B-swizzled [128 x 64] Q chunk + [256 x 64] G chunk
+//            per pipeline stage (4 stages x 48 KiB), mbarrier complete_tx.
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256,
+//            K=16), fp32 accumulators in TMEM, 2 accumulator stages x 256 columns; tcgen05.commit
+//            releases smem stages and publishes finished accumulators.
+//   warps 2-5 epilogue: thread <-> query row (TMEM lane).  tcgen05.ld 32 columns at a time,
+//            s = (acc * inv_norm[g]) * inv_norm[q], strict threshold test s > tau against the
+//            thread's running k-th best; survivors are appended to the query's candidate buffer in
+//            global memory (L2-resident, rarely written).  When a buffer fills, the warp
+//            cooperatively selects the exact top-k (bitwise radix descent on 64-bit keys held in
+//            registers), compacts the buffer and tightens tau.
+// Per (query, CTA) the gallery rows arrive in increasing order, so on an exact score tie the
+// earlier row is already buffered and the strict test implements "score desc, row asc".
+// select.cu merges the per-CTA lists.
+//
+// Roofline: tensor-core bound, 2 * b * n * d_pad FLOP per launch.
+#include <cuda.h>
+
 #include "internal.h"
+
 namespace mmr {
-int plan_gemm(int64_t, int, int, int, int, GemmPlan*) { return fail(MMR_EUNSUP, "gemm path not built"); }
-int launch_gemm_topk(const void*, const float*, int64_t, int, const void*, const float*, int, int, const int64_t*,
-                     const GemmPlan&, uint64_t*, int32_t*, cudaStream_t) { return fail(MMR_EUNSUP, "gemm path not built"); }
+namespace {
+
+constexpr int kBlockM = 128;          // queries per CTA tile (TMEM lanes)
+constexpr int kBlockN = 256;          // gallery rows per accumulator stage (UMMA N)
+constexpr int kBlockK = 64;           // bf16 elements per smem chunk row = 128 B (swizzle span)
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * kBlockN;  // 512
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
+constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kNumThreads = 192;                 // 6 warps
+constexpr int kEpiThreads = 128;
+
+struct __align__(16) SmemAux {
+  float ginv[kAccStages][kBlockN];  // first: read as float4
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + static_cast<size_t>(kStages) * kStageBytes + sizeof(SmemAux);
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, 128-byte swizzle, rows of 64 bf16: 8-row atoms 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address  [0,14)
+  d |= static_cast<uint64_t>(0) << 16;                      // leading byte offset (ignored for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // stride byte offset [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                      // layout: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// candidate entry in global memory: {fp32 score bits, local gallery row}
+__device__ __forceinline__ uint64_t entry_key(uint2 e) { return make_key(__uint_as_float(e.x), e.y); }
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative exact top-k of one query's candidate buffer (cnt <= E*32 entries).
+// Returns the new strict threshold (score of the k-th best); the buffer front holds the k best.
+// ---------------------------------------------------------------------------------------------
+template <int E>
+__device__ __forceinline__ float warp_compact(uint2* buf, int cnt, int k, int lane) {
+  uint64_t key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    key[e] = (i < cnt) ? entry_key(buf[i]) : 0ull;
+  }
+  __syncwarp();
+  // largest T with count(key >= T) >= k, found MSB first; stop as soon as the count is exactly k
+  uint64_t prefix = 0;
+  for (int bit = 63; bit >= 0; --bit) {
+    const uint64_t cand = prefix | (1ull << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (key[e] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) {
+      prefix = cand;
+      if (c == k) break;
+    }
+  }
+  // keep key >= prefix (exactly k of them when cnt >= k), compacting in place
+  uint64_t kmin = ~0ull;
+  int base = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool keep = key[e] >= prefix && key[e] != 0ull;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      buf[pos] = make_uint2(__float_as_uint(key_score(key[e])), key_row(key[e]));
+      kmin = key[e] < kmin ? key[e] : kmin;
+    }
+    base += __popc(m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, kmin, o);
+    kmin = other < kmin ? other : kmin;
+  }
+  __syncwarp();
+  return key_score(kmin);
+}
+
+// generic version for large k: keys are re-read from the (L2-resident) buffer every pass
+__device__ __noinline__ float warp_compact_generic(uint2* buf, int cnt, int k, int lane, uint2* scratch) {
+  uint64_t prefix = 0;
+  for (int bit = 63; bit >= 0; --bit) {
+    const uint64_t cand = prefix | (1ull << bit);
+    int c = 0;
+    for (int i = lane; i < cnt; i += 32) c += (entry_key(buf[i]) >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) {
+      prefix = cand;
+      if (c == k) break;
+    }
+  }
+  // stable in-place compaction: a kept element never moves to a higher index, and rounds proceed
+  // in increasing index order, so reads of later rounds are never clobbered
+  uint64_t kmin = ~0ull;
+  int base = 0;
+  for (int i0 = 0; i0 < cnt; i0 += 32) {
+    const int i = i0 + lane;
+    const uint2 e = (i < cnt) ? buf[i] : make_uint2(0u, 0u);
+    const uint64_t key = (i < cnt) ? entry_key(e) : 0ull;
+    const bool keep = key >= prefix && key != 0ull;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) {
+      buf[base + __popc(m & ((1u << lane) - 1u))] = e;
+      kmin = key < kmin ? key : kmin;
+    }
+    base += __popc(m);
+    __syncwarp();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, kmin, o);
+    kmin = other < kmin ? other : kmin;
+  }
+  return key_score(kmin);
+}
+
+__device__ __forceinline__ float warp_compact_dispatch(uint2* buf, int cnt, int k, int cap, int lane) {
+  if (cap == 512) return warp_compact<16>(buf, cnt, k, lane);
+  if (cap == 1024) return warp_compact<32>(buf, cnt, k, lane);
+  return warp_compact_generic(buf, cnt, k, lane, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                 const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
+                 int k, int cap, int m_tiles, int n_parts, int tiles_per_part, int tiles_total,
+                 uint2* __restrict__ cand, int32_t* __restrict__ counts) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SmemAux* aux = reinterpret_cast<SmemAux*>(smem + static_cast<size_t>(kStages) * kStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x % m_tiles;
+  const int part = blockIdx.x / m_tiles;
+  const int tile_begin = part * tiles_per_part;
+  const int tile_end = min(tile_begin + tiles_per_part, tiles_total);
+  const int num_tiles = tile_end - tile_begin;
+  const int num_kc = d_pad / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_g);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&aux->full[s], 1);
+      mbar_init(&aux->empty[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&aux->tmem_full[s], 1);
+      mbar_init(&aux->tmem_empty[s], kEpiThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&aux->tmem_base)),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = aux->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int n0 = (tile_begin + t) * kBlockN;
+        for (int kc = 0; kc < num_kc; ++kc) {
+          mbar_wait(&aux->empty[stage], phase ^ 1u);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&aux->full[stage], kStageBytes);
+          tma_load_2d(&tmap_q, &aux->full[stage], sa, kc * kBlockK, m_tile * kBlockM);
+          tma_load_2d(&tmap_g, &aux->full[stage], sb, kc * kBlockK, n0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1u;
+        mbar_wait(&aux->tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBlockN);
+        for (int kc = 0; kc < num_kc; ++kc) {
+          mbar_wait(&aux->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t adesc = make_umma_desc(sa);
+          const uint64_t bdesc = make_umma_desc(sb);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
+            umma_f16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc + static_cast<uint64_t>(kk * 2), idesc,
+                     (kc | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&aux->empty[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&aux->tmem_full[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue: scale + threshold + top-k =====================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const int q = m_tile * kBlockM + row_in_tile;
+    const bool q_ok = q < b;
+    const float qinv = q_ok ? q_inv[q] : 0.f;
+    uint2* buf = cand + (static_cast<int64_t>(q_ok ? q : 0) * n_parts + part) * cap;
+    int cnt = 0;
+    float tau = q_ok ? -INFINITY : INFINITY;
+    const int epi_tid = threadIdx.x - 64;  // 0..127
+    const int64_t range_end = min(static_cast<int64_t>(tile_end) * kBlockN, n);
+
+    for (int t = 0; t < num_tiles; ++t) {
+      const int acc = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1u;
+      const int64_t n0 = static_cast<int64_t>(tile_begin + t) * kBlockN;
+      // stage this tile's gallery inverse norms (NaN marks rows outside the range: never a hit)
+      for (int i = epi_tid; i < kBlockN; i += kEpiThreads) {
+        const int64_t r = n0 + i;
+        aux->ginv[acc][i] = (r < range_end) ? __ldg(inv_norm + r) : __int_as_float(0x7FC00000);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&aux->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        const float4* gi4 = reinterpret_cast<const float4*>(&aux->ginv[acc][c * 32]);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 gi = gi4[j4];
+          const float gs[4] = {gi.x, gi.y, gi.z, gi.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 * 4 + jj;
+            const float s = (__uint_as_float(v[j]) * gs[jj]) * qinv;
+            if (s > tau) {
+              buf[cnt] = make_uint2(__float_as_uint(s), static_cast<uint32_t>(n0 + c * 32 + j));
+              ++cnt;
+            }
+          }
+        }
+        // make room for the next 32 columns: compact every query of this warp whose buffer is nearly full
+        uint32_t need = __ballot_sync(0xffffffffu, cnt > cap - 32);
+        while (need != 0u) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1u;
+          uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
+          const int scnt = __shfl_sync(0xffffffffu, cnt, src);
+          __syncwarp();
+          const float new_tau = warp_compact_dispatch(sbuf, scnt, k, cap, lane);
+          if (lane == src) {
+            cnt = k;
+            tau = new_tau;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aux->tmem_empty[acc]);
+    }
+    // final exact top-k per query so that select.cu merges short lists
+    {
+      uint32_t need = __ballot_sync(0xffffffffu, q_ok && cnt > k);
+      while (need != 0u) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1u;
+        uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
+        const int scnt = __shfl_sync(0xffffffffu, cnt, src);
+        __syncwarp();
+        (void)warp_compact_dispatch(sbuf, scnt, k, cap, lane);
+        if (lane == src) cnt = k;
+      }
+      if (q_ok) counts[static_cast<int64_t>(q) * n_parts + part] = cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeFn* out) {
+  static EncodeFn cached = nullptr;
+  if (cached == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MMR_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+      return fail(MMR_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cached = reinterpret_cast<EncodeFn>(fn);
+  }
+  *out = cached;
+  return MMR_OK;
+}
+
+// (rows, d_pad) bf16 row-major -> 2-D map, box = [box_rows x 64 elements], 128-byte swizzle, zero OOB fill
+int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int d_pad, int box_rows) {
+  EncodeFn enc;
+  MMR_TRY(get_encode_fn(&enc));
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(d_pad) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MMR_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return MMR_OK;
+}
+
+}  // namespace
+
+int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
+  if (k < 1 || k > MMR_MAX_K) return fail(MMR_EUNSUP, "gemm: k must be in [1, 1024]");
+  if (n < 1) return fail(MMR_EINVAL, "gemm: empty gallery");
+  if (d_pad % kBlockK != 0) return fail(MMR_EINVAL, "gemm: d_pad must be a multiple of 64");
+  const int m_tiles = (b + kBlockM - 1) / kBlockM;
+  const int64_t tiles_total = (n + kBlockN - 1) / kBlockN;
+  // pick the number of gallery parts so that m_tiles * parts fills whole waves of SMs
+  int best_parts = 1;
+  double best_eff = -1.0;
+  for (int w = 1; w <= 8; ++w) {
+    int64_t parts = static_cast<int64_t>(w) * num_sms / m_tiles;
+    if (parts < 1) parts = 1;
+    if (parts > tiles_total) parts = tiles_total;
+    const int64_t ctas = parts * m_tiles;
+    const int64_t waves = (ctas + num_sms - 1) / num_sms;
+    const double eff = static_cast<double>(ctas) / static_cast<double>(waves * num_sms);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best_parts = static_cast<int>(parts);
+    }
+    if (eff >= 0.97 || parts == tiles_total) break;
+  }
+  const int tiles_per_part = static_cast<int>((tiles_total + best_parts - 1) / best_parts);
+  const int n_parts = static_cast<int>((tiles_total + tiles_per_part - 1) / tiles_per_part);
+  int cap = 512;
+  if (k > 128) cap = 1024;
+  if (k > 256) cap = 4096;
+  plan->m_tiles = m_tiles;
+  plan->n_parts = n_parts;
+  plan->ctas_per_mtile = tiles_per_part;  // (re-used field: tiles per part)
+  plan->cap = cap;
+  plan->cand_bytes = static_cast<size_t>(b) * n_parts * cap * sizeof(uint2);
+  plan->count_bytes = static_cast<size_t>(b) * n_parts * sizeof(int32_t);
+  return MMR_OK;
+}
+
+int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int d_pad, const void* q_bf16,
+                     const float* q_inv, int b, int k, const int64_t* /*exclude_local: applied by select*/,
+                     const GemmPlan& plan, uint64_t* cand, int32_t* counts, cudaStream_t stream) {
+  CUtensorMap tmap_q, tmap_g;
+  MMR_TRY(make_tmap(&tmap_q, q_bf16, b, d_pad, kBlockM));
+  MMR_TRY(make_tmap(&tmap_g, emb_bf16, n, d_pad, kBlockN));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMR_CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kSmemBytes)));
+    attr_set = true;
+  }
+  const int tiles_total = static_cast<int>((n + kBlockN - 1) / kBlockN);
+  const int grid = plan.m_tiles * plan.n_parts;
+  gemm_topk_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k,
+                                                              plan.cap, plan.m_tiles, plan.n_parts,
+                                                              plan.ctas_per_mtile, tiles_total,
+                                                              reinterpret_cast<uint2*>(cand), counts);
+  MMR_CUDA_TRY(cudaGetLastError());
+  return MMR_OK;
+}
+
 }  // namespace mmr

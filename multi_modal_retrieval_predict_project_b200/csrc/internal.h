@@ -75,14 +75,15 @@ struct GemmPlan {
   int cap;              // candidate capacity per (query, part)
   size_t cand_bytes;    // candidate buffer bytes
   size_t count_bytes;   // per-(query, part) counts
-  int m_tiles, ctas_per_mtile;
+  int m_tiles, ctas_per_mtile;  // ctas_per_mtile holds the gallery tiles per part
 };
 int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan);
 int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int d_pad, const void* q_bf16,
                      const float* q_inv, int b, int k, const int64_t* exclude_local, const GemmPlan& plan,
                      uint64_t* cand, int32_t* counts, cudaStream_t stream);
-int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int k_out,
-                      int64_t row_offset, float* out_scores, int64_t* out_rows, cudaStream_t stream);
+int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int per_part,
+                      int k_out, int64_t row_offset, const int64_t* exclude_local, float* out_scores,
+                      int64_t* out_rows, cudaStream_t stream);
 
 // rerank.cu
 int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pad, int64_t row_offset,

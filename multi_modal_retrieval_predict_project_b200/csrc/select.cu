@@ -22,17 +22,22 @@ struct KeySourceFlat {  // keys contiguous per query
   __device__ __forceinline__ uint64_t get(int q, int64_t i) const { return keys[q * per_query + i]; }
 };
 
-struct KeySourceVar {  // (b, n_parts, cap) with per-(query, part) counts
-  const uint64_t* cand;
+struct KeySourceVar {  // GEMM candidates: (b, n_parts, cap) raw {score bits, local row}, first counts[] valid
+  const uint2* cand;
   const int32_t* counts;
   int n_parts;
   int cap;
-  __device__ __forceinline__ int64_t count(int) const { return static_cast<int64_t>(n_parts) * cap; }
+  int per_part;            // entries considered per part (the kernel leaves <= k valid ones)
+  const int64_t* exclude;  // optional (b) local row to drop per query
+  __device__ __forceinline__ int64_t count(int) const { return static_cast<int64_t>(n_parts) * per_part; }
   __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
-    const int part = static_cast<int>(i / cap);
-    const int j = static_cast<int>(i - static_cast<int64_t>(part) * cap);
+    const int part = static_cast<int>(i / per_part);
+    const int j = static_cast<int>(i - static_cast<int64_t>(part) * per_part);
     const int c = counts[static_cast<int64_t>(q) * n_parts + part];
-    return j < (c < cap ? c : cap) ? cand[(static_cast<int64_t>(q) * n_parts + part) * cap + j] : 0ull;
+    if (j >= (c < per_part ? c : per_part)) return 0ull;
+    const uint2 e = cand[(static_cast<int64_t>(q) * n_parts + part) * cap + j];
+    if (exclude != nullptr && static_cast<int64_t>(e.y) == exclude[q]) return 0ull;
+    return make_key(__uint_as_float(e.x), e.y);
   }
 };
 
@@ -128,10 +133,11 @@ int launch_select_keys(const uint64_t* keys, int b, int64_t keys_per_query, int 
   return launch_select(src, b, keys_per_query, k_out, row_offset, out_scores, out_rows, nullptr, stream);
 }
 
-int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int k_out,
-                      int64_t row_offset, float* out_scores, int64_t* out_rows, cudaStream_t stream) {
-  KeySourceVar src{cand, counts, n_parts, cap};
-  return launch_select(src, b, static_cast<int64_t>(n_parts) * cap, k_out, row_offset, out_scores, out_rows,
+int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int per_part,
+                      int k_out, int64_t row_offset, const int64_t* exclude_local, float* out_scores,
+                      int64_t* out_rows, cudaStream_t stream) {
+  KeySourceVar src{reinterpret_cast<const uint2*>(cand), counts, n_parts, cap, per_part, exclude_local};
+  return launch_select(src, b, static_cast<int64_t>(n_parts) * per_part, k_out, row_offset, out_scores, out_rows,
                        nullptr, stream);
 }
 
