@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the retrieval hot path: exact cosine top-K search + label/KG rerank.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (B200 kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Metric (BASELINE.json): queries/s for top-100 cosine + rerank over a 10M x 512 bf16 gallery.
+One "step" = one batch of queries through search -> top-K -> rerank.  At N > 1 the gallery is
+row-sharded over the ranks (strong scaling: total rows fixed), each rank searches its shard, then
+NCCL all-gather + on-device K-way merge + rerank.  Also reported on rank 0 at N = 1: the batch-1
+top-10 p50 latency (HBM-scan regime) and the CPU baseline.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec top-100 cosine+rerank, 10M x 512 bf16 gallery"
+UNIT = "queries/s"
+SEED = 2709
+CHUNK = 1 << 20  # rows per generation chunk (global alignment => shards see the same data for any N)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--kg-dim", type=int, default=300)
+    ap.add_argument("--algo", default="auto")
+    ap.add_argument("--no-rerank", action="store_true")
+    ap.add_argument("--latency-queries", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (pynvml) during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake", 0x100: "display_clock"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons - {"gpu_idle"})}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data (device side; counter-style: chunk c is generated from seed SEED + c)
+# ------------------------------------------------------------------------------------------------
+def gen_rows(lo, hi, width, seed_base, device, dtype, normalize=False):
+    import torch
+    out = torch.empty((hi - lo, width), dtype=dtype, device=device)
+    c0 = lo // CHUNK
+    c1 = (hi - 1) // CHUNK if hi > lo else c0 - 1
+    for c in range(c0, c1 + 1):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed_base + c)
+        blk = torch.randn((CHUNK, width), generator=g, device=device, dtype=torch.float32)
+        if normalize:
+            blk = blk / (blk.norm(dim=1, keepdim=True) + 1e-12)
+        a, b_ = max(lo, c * CHUNK), min(hi, (c + 1) * CHUNK)
+        out[a - lo:b_ - lo] = blk[a - c * CHUNK:b_ - c * CHUNK].to(dtype)
+        del blk
+    return out
+
+
+def gen_masks(lo, hi, device, n_labels=43, p=0.08):
+    import torch
+    out = torch.empty((hi - lo,), dtype=torch.int64, device=device)
+    c0 = lo // CHUNK
+    c1 = (hi - 1) // CHUNK if hi > lo else c0 - 1
+    w = (1 << torch.arange(n_labels, device=device, dtype=torch.int64))
+    for c in range(c0, c1 + 1):
+        g = torch.Generator(device=device)
+        g.manual_seed(SEED + 500_000 + c)
+        bits = (torch.rand((CHUNK, n_labels), generator=g, device=device) < p).to(torch.int64)
+        m = (bits * w).sum(dim=1)
+        a, b_ = max(lo, c * CHUNK), min(hi, (c + 1) * CHUNK)
+        out[a - lo:b_ - lo] = m[a - c * CHUNK:b_ - c * CHUNK]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's exact path on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup):
+    """The reference's own CPU path (sklearn-style normalise + sgemm + np.argsort, then
+    Reranker.rerank) restated by oracle/ (the reference is Python and /root/reference does not
+    travel to the GPU box => kind "port").  Bounded sample: a 1/50 row slice of the gallery and 64
+    queries per step for the search (exact search cost is linear in rows => scaled to the full
+    gallery), and the per-query rerank cost measured on 100-candidate lists."""
+    import tempfile
+    import numpy as np
+    from multi_modal_retrieval_predict_project_b200 import synth
+    from oracle import rerank as orr
+    from oracle import search as osr
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    frac = 50
+    n_s = max(1000, args.rows // frac)
+    bq = 64
+    rng = np.random.default_rng(SEED)
+    g = osr.to_bf16_round(rng.standard_normal((n_s, args.dim), dtype=np.float32))
+    q = osr.to_bf16_round(rng.standard_normal((bq, args.dim), dtype=np.float32))
+    # rerank tables for the sample (labels CSV + KG dir exactly as the reference reads them)
+    tmp = tempfile.mkdtemp(prefix="mmr_cpu_")
+    n_rec = 4000
+    ids = synth.make_ids(n_rec)
+    qids = synth.make_ids(8, "t")
+    labels = synth.make_labels(n_rec + 8)
+    csv = synth.write_labels_csv(os.path.join(tmp, "labels.csv"), ids + qids, labels)
+    kg_dir = synth.write_kg(os.path.join(tmp, "kg"), ids + qids, synth.label_names(), d_kg=args.kg_dim)
+    rer = orr.OracleReranker(kg_dir, csv)
+
+    def one_step():
+        t0 = time.perf_counter()
+        sim = osr.cosine_similarity(q, g)                       # retrieval_overlap.py:85
+        top = [np.argsort(sim[i])[::-1][:args.k] for i in range(bq)]  # :90
+        t_search = time.perf_counter() - t0
+        t_rr = 0.0
+        if not args.no_rerank:
+            t1 = time.perf_counter()
+            for i in range(4):                                  # 4 queries x K candidates
+                cand = [int(j) % n_rec for j in top[i]]
+                rer.rerank(qids[i], [ids[j] for j in cand], candidate_embs=g[top[i]], query_emb=q[i], topk=args.k)
+            t_rr = (time.perf_counter() - t1) / 4
+        # seconds per query on the FULL gallery: search scales with rows, rerank does not
+        per_query = (t_search / bq) * (args.rows / n_s) + t_rr
+        return per_query, t_search, t_rr
+
+    for _ in range(max(1, min(warmup, 2))):
+        one_step()
+    per = [one_step() for _ in range(max(1, steps))]
+    pq = float(np.median([p[0] for p in per]))
+    sample = (f"{bq} queries x {n_s}-row slice (1/{frac} of the gallery, search time scaled x{args.rows / n_s:.0f}) "
+              f"+ rerank of {args.k} candidates timed on 4 queries; numpy/BLAS threads={cores}")
+    return {"value": 1.0 / pq, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "search_s_per_query_full": float(np.median([p[1] for p in per])) / bq * (args.rows / n_s),
+            "rerank_s_per_query": float(np.median([p[2] for p in per]))}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.rows}x{args.dim} bf16 gallery, query batch {args.batch}, top-{args.k}"
+                          + ("" if args.no_rerank else " + label/KG rerank (alpha,beta,gamma=0.6,0.25,0.15)"),
+              "rows": args.rows, "dim": args.dim, "batch": args.batch, "k": args.k, "rerank": not args.no_rerank,
+              "sharding": f"row-sharded x{world}" if world > 1 else "single shard",
+              "l2_policy": "inputs larger than L2: the gallery shard (>= 1.28 GB) is streamed from HBM every step"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        cb = cpu_reference_run(args, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / cb["value"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, _lib
+    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher, shard_bounds
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # ---------------- data: this rank's gallery shard + replicated rerank tables ----------------
+    lo, hi = shard_bounds(args.rows, world, rank)
+    gallery = gen_rows(lo, hi, args.dim, SEED, dev, torch.bfloat16)
+    engine = B200RetrievalEngine.from_arrays(gallery, dtype="bfloat16", device=local_rank, row_offset=lo, borrow=True,
+                                             keep_host=False, algo=args.algo)
+    searcher = ShardedSearcher(engine)
+    b, k = args.batch, args.k
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(SEED + 900_000)
+    q_dev = torch.randn((b, args.dim), generator=gq, device=dev).to(torch.bfloat16).float()  # bf16-rounded values
+    q_host = q_dev.cpu().pin_memory()
+    reranker = None
+    if not args.no_rerank:
+        n_rec = args.rows + b  # records: gallery rows then the query records
+        masks = gen_masks(0, n_rec, dev)
+        kg = gen_rows(0, n_rec, args.kg_dim, SEED + 700_000, dev, torch.float32, normalize=True)
+        reranker = Reranker.from_tables(masks, kg, device=local_rank)
+        del masks, kg
+        q_rec = torch.arange(args.rows, args.rows + b, device=dev, dtype=torch.int64)
+    torch.cuda.synchronize()
+
+    def step(q):
+        rows, scores = searcher.search(q, k)
+        if reranker is None:
+            return rows, scores
+        order, sc = searcher.rerank(reranker, q, rows, q_rec, rows, topk=k)  # record index == global row
+        return rows, order, sc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step(q_dev)
+    barrier()
+
+    # ---------------- timed region: device-resident inputs -----------------------------------
+    sampler = ClockSampler(local_rank)
+    engine.profile(True)
+    launches0 = lib.mmr_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(q_dev)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = lib.mmr_launch_count() - launches0
+    kern_ms, kern_n = engine.profile(False)
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = b * args.steps / (elapsed_ms / 1e3)
+
+    # ---------------- end to end: pinned host queries in, host results out, every step ---------
+    out_host = None
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        qd = q_host.to(dev, non_blocking=True)
+        res = step(qd)
+        if out_host is None:
+            out_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
+        for h, r in zip(out_host, res):
+            h.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    d2h = sum(h.numel() * h.element_size() for h in out_host)
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = {"value": b * args.steps / float(t.item()), "unit": UNIT,
+           "h2d_bytes_per_step": q_host.numel() * q_host.element_size(), "d2h_bytes_per_step": d2h}
+
+    # ---------------- roofline of the dominant kernel ------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    n_local = hi - lo
+    kern_avg_ms = kern_ms / max(kern_n, 1)
+    flops = 2.0 * b * n_local * args.dim
+    use_gemm = (args.algo == "gemm") or (args.algo == "auto" and b >= 16 and n_local >= 4096)
+    if use_gemm:
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = flops / (kern_avg_ms / 1e3) / 1e12 if kern_avg_ms > 0 else 0.0
+        roofline = {"kernel": "gemm_topk_kernel (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                    if peaks else "fallback", "peak_burst": peaks.get("bf16_tflops"),
+                    "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_ms / elapsed_ms if elapsed_ms else None,
+                    "algorithmic_flops_per_launch": flops}
+    else:
+        peak = peaks.get("hbm_gbs", 6650.0)
+        byts = n_local * args.dim * 2.0 + 4.0 * n_local
+        groups = -(-b // 4)
+        ach = byts * groups / (kern_avg_ms / 1e3) / 1e9 if kern_avg_ms > 0 else 0.0
+        roofline = {"kernel": "scan_topk_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "kernel_ms": kern_avg_ms,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+
+    # ---------------- batch-1 latency (HBM-scan regime) + CPU baseline: rank 0, N = 1 only -------
+    if world == 1:
+        nlat = args.latency_queries
+        if nlat > 0:
+            q1 = q_host[:1].numpy()
+            for _ in range(5):
+                engine.search(q1, 10, algo="scan")
+            engine.profile(True)
+            lat = []
+            for i in range(nlat):
+                qi = q_host[i % b:i % b + 1].numpy()
+                t0 = time.perf_counter()
+                engine.search(qi, 10, algo="scan")       # host in, host out: launch + H2D + D2H included
+                lat.append(time.perf_counter() - t0)
+            sms, sn = engine.profile(False)
+            lat.sort()
+            scan_ms = sms / max(sn, 1)
+            byts = n_local * args.dim * 2.0 + 4.0 * n_local
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            line["batch1_top10"] = {"p50_ms": 1e3 * lat[len(lat) // 2], "p99_ms": 1e3 * lat[int(len(lat) * 0.99)],
+                                    "queries": nlat, "scan_kernel_ms": scan_ms,
+                                    "roofline": {"bound": "hbm", "achieved": byts / (scan_ms / 1e3) / 1e9,
+                                                 "peak": hbm, "unit": "GB/s",
+                                                 "frac": byts / (scan_ms / 1e3) / 1e9 / hbm,
+                                                 "algorithmic_bytes_per_launch": byts}}
+        if rank == 0 and not args.no_cpu_baseline:
+            del gallery
+            line["cpu_baseline"] = cpu_reference_run(args, 3, 1)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

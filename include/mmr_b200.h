@@ -62,6 +62,9 @@ typedef struct mmr_rerank_tables mmr_rerank_tables; /* label bitmasks + KG vecto
 
 int         mmr_abi_version(void);
 const char* mmr_last_error(void);
+/* Number of kernels this library has launched in this process (all handles, all streams); the
+ * benchmark reports the difference across its timed region as `gpu_launches`. */
+int64_t     mmr_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * Gallery.  Replaces RetrievalEngine.__init__ (Retrieval/retrieval.py:24-32): the gallery is
@@ -83,6 +86,12 @@ int mmr_index_device_ptrs(const mmr_index* index, const void** emb, const float*
 /* RetrievalEngine.get_embeddings_for_ids (Retrieval/retrieval.py:41-50): gather rows by GLOBAL
  * row id into `out` (m x d fp32); a row id outside the shard (e.g. -1 = unknown id) yields zeros. */
 int mmr_index_get_rows(const mmr_index* index, const int64_t* rows, int64_t m, float* out, void* stream);
+
+/* Live kernel timing for roofline accounting: while enabled, mmr_search brackets its dominant
+ * kernel (the GEMM or the scan) with CUDA events on the caller's stream.  Calling with enable = 0
+ * (or 1 again) synchronises, returns the summed duration in milliseconds and the number of timed
+ * launches since the previous call (either pointer may be NULL), and resets the counters. */
+int mmr_index_profile(mmr_index* index, int32_t enable, double* kernel_ms_sum, int32_t* kernel_launches);
 
 /* ---------------------------------------------------------------------------------------
  * Exact cosine search + top-K.  Replaces the exact form cosine_similarity(Q, G) +

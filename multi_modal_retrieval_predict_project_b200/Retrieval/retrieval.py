@@ -205,6 +205,13 @@ class B200RetrievalEngine(RetrievalEngine):
         _lib.check(self._lib.mmr_index_info(self._handle, None, None, None, None, None, None, _lib.C.byref(v)))
         return v.value
 
+    def profile(self, enable: bool):
+        """Start/stop live CUDA-event timing of the dominant search kernel; returns
+        ``(summed_ms, launches)`` accumulated since the previous call (mmr_index_profile)."""
+        ms, cnt = _lib.C.c_double(), _lib.C.c_int32()
+        _lib.check(self._lib.mmr_index_profile(self._handle, 1 if enable else 0, _lib.C.byref(ms), _lib.C.byref(cnt)))
+        return ms.value, cnt.value
+
     # -- batched search (the hot path) ----------------------------------------------------------
     def search(self, queries, K: int, exclude_rows=None, algo: Optional[str] = None):
         """Exact top-K for a batch.  ``queries``: numpy ``(B, D)`` / ``(D,)`` (host) or a torch

@@ -31,6 +31,8 @@ _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
     "mmr_abi_version": [],
     "mmr_last_error": [],
+    "mmr_launch_count": [],
+    "mmr_index_profile": [_vp, _i32, C.POINTER(_f64), C.POINTER(_i32)],
     "mmr_index_create": [C.POINTER(_vp), _vp, _i64, _i32, _i32, _i32, _i64, _i32, _i32, _vp],
     "mmr_index_destroy": [_vp],
     "mmr_index_info": [_vp, C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
@@ -47,7 +49,7 @@ SIGNATURES = {
     "mmr_metrics": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "mmr_label_relevance": [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, _vp],
 }
-_RESTYPES = {"mmr_last_error": C.c_char_p}
+_RESTYPES = {"mmr_last_error": C.c_char_p, "mmr_launch_count": C.c_int64}
 
 
 class MMRError(RuntimeError):

@@ -3,6 +3,7 @@
 // Host-side orchestration only: argument checks, host<->device staging, workspace management,
 // kernel sequencing on the caller's stream.  No compute happens on the CPU and there is no CPU
 // fallback: every path ends in a kernel launch or an error code.
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,6 +26,10 @@ struct mmr_index {
   float* inv_norm = nullptr;
   std::mutex mu;  // search is re-entrant per handle by serialising on the handle's workspaces
   mmr::DeviceBuf q_in, q_store, q_f32, q_inv, scratch, excl_in, excl_local, partial, counts, out_scores, out_rows;
+  // live kernel timing (mmr_index_profile)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_start, ev_stop;
+  size_t ev_used = 0;
 };
 
 struct mmr_rerank_tables {
@@ -39,6 +44,8 @@ struct mmr_rerank_tables {
 namespace mmr {
 
 static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -204,6 +211,27 @@ extern "C" {
 
 int mmr_abi_version(void) { return MMR_ABI_VERSION; }
 const char* mmr_last_error(void) { return g_last_error.c_str(); }
+int64_t mmr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mmr_index_profile(mmr_index* ix, int32_t enable, double* kernel_ms_sum, int32_t* kernel_launches) {
+  MMR_REQUIRE(ix != nullptr, "mmr_index_profile: index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  DeviceGuard guard(ix->device);
+  double sum = 0.0;
+  if (ix->ev_used > 0) {
+    MMR_CUDA_TRY(cudaEventSynchronize(ix->ev_stop[ix->ev_used - 1]));
+    for (size_t i = 0; i < ix->ev_used; ++i) {
+      float ms = 0.f;
+      MMR_CUDA_TRY(cudaEventElapsedTime(&ms, ix->ev_start[i], ix->ev_stop[i]));
+      sum += ms;
+    }
+  }
+  if (kernel_ms_sum) *kernel_ms_sum = sum;
+  if (kernel_launches) *kernel_launches = static_cast<int32_t>(ix->ev_used);
+  ix->ev_used = 0;
+  ix->profiling = enable != 0;
+  return MMR_OK;
+}
 
 int mmr_index_create(mmr_index** out, const void* emb, int64_t n, int32_t d, int32_t dtype_in, int32_t dtype_store,
                      int64_t row_offset, int32_t device, int32_t flags, void* stream_v) {
@@ -306,6 +334,8 @@ int mmr_index_destroy(mmr_index* ix) {
   for (DeviceBuf* b : {&ix->q_in, &ix->q_store, &ix->q_f32, &ix->q_inv, &ix->scratch, &ix->excl_in, &ix->excl_local, &ix->partial,
                        &ix->counts, &ix->out_scores, &ix->out_rows})
     b->release();
+  for (cudaEvent_t e : ix->ev_start) cudaEventDestroy(e);
+  for (cudaEvent_t e : ix->ev_stop) cudaEventDestroy(e);
   delete ix;
   return MMR_OK;
 }
@@ -377,7 +407,7 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     globalize_exclude_kernel<<<(b + 127) / 128, 128, 0, stream>>>(static_cast<const int64_t*>(d_ex_in), b,
                                                                   ix->row_offset, ix->n,
                                                                   ix->excl_local.as<int64_t>());
-    MMR_CUDA_TRY(cudaGetLastError());
+    MMR_LAUNCHED();
     d_excl = ix->excl_local.as<int64_t>();
   }
 
@@ -394,6 +424,20 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     d_rows = ix->out_rows.as<int64_t>();
   }
 
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ix->profiling) {
+    if (ix->ev_used == ix->ev_start.size()) {
+      cudaEvent_t a, c;
+      MMR_CUDA_TRY(cudaEventCreate(&a));
+      MMR_CUDA_TRY(cudaEventCreate(&c));
+      ix->ev_start.push_back(a);
+      ix->ev_stop.push_back(c);
+    }
+    ev0 = ix->ev_start[ix->ev_used];
+    ev1 = ix->ev_stop[ix->ev_used];
+    ++ix->ev_used;
+  }
+
   int use = algo;
   if (use == MMR_ALGO_AUTO) use = (ix->dtype == MMR_BF16 && b >= 16 && ix->n >= 4096) ? MMR_ALGO_GEMM : MMR_ALGO_SCAN;
 
@@ -403,8 +447,10 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     MMR_TRY(plan_gemm(ix->n, ix->d_pad, b, k_eff, ix->num_sms, &gp));
     MMR_TRY(ix->partial.ensure(gp.cand_bytes));
     MMR_TRY(ix->counts.ensure(gp.count_bytes));
+    if (ev0) MMR_CUDA_TRY(cudaEventRecord(ev0, stream));
     MMR_TRY(launch_gemm_topk(ix->emb, ix->inv_norm, ix->n, ix->d_pad, ix->q_store.p, ix->q_inv.as<float>(), b, k_eff,
                              d_excl, gp, ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), stream));
+    if (ev1) MMR_CUDA_TRY(cudaEventRecord(ev1, stream));
     MMR_TRY(launch_select_var(ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), b, gp.n_parts, gp.cap, k_eff, k,
                               ix->row_offset, d_excl, d_scores, d_rows, stream));
   } else {
@@ -422,8 +468,10 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     ScanPlan sp;
     MMR_TRY(plan_scan(ix->n, ix->d_pad, ix->dtype, b, k, ix->num_sms, &sp));
     MMR_TRY(ix->partial.ensure(sp.partial_bytes));
+    if (ev0) MMR_CUDA_TRY(cudaEventRecord(ev0, stream));
     MMR_TRY(launch_scan(ix->emb, ix->dtype, ix->inv_norm, ix->n, ix->d_pad, q_f32, ix->q_inv.as<float>(), b, k, d_excl,
                         sp, ix->partial.as<uint64_t>(), stream));
+    if (ev1) MMR_CUDA_TRY(cudaEventRecord(ev1, stream));
     MMR_TRY(launch_select_keys(ix->partial.as<uint64_t>(), b, static_cast<int64_t>(sp.n_parts) * sp.kp, k,
                                ix->row_offset, d_scores, d_rows, stream));
   }

@@ -16,6 +16,7 @@ namespace mmr {
 // ---------------------------------------------------------------------------------------------
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
+void count_launch();  // every kernel launch site calls this (mmr_launch_count)
 
 #define MMR_CUDA_TRY(expr)                                                                      \
   do {                                                                                          \
@@ -25,6 +26,13 @@ int fail(int code, const std::string& msg);
                          std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
                              ":" + std::to_string(__LINE__) + ")");                             \
     }                                                                                           \
+  } while (0)
+
+// after a <<<...>>> launch: count it and surface launch errors
+#define MMR_LAUNCHED()          \
+  do {                          \
+    ::mmr::count_launch();      \
+    MMR_CUDA_TRY(cudaGetLastError()); \
   } while (0)
 
 #define MMR_TRY(expr)             \

@@ -518,7 +518,7 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
                                                               plan.cap, plan.m_tiles, plan.n_parts,
                                                               plan.ctas_per_mtile, tiles_total,
                                                               reinterpret_cast<uint2*>(cand), counts);
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 

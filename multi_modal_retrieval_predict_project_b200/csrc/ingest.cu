@@ -128,7 +128,7 @@ int launch_ingest(const void* src, int dtype_in, int64_t n, int d, int64_t src_l
   } else {
     return fail(MMR_EINVAL, "ingest: unsupported dtype combination");
   }
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 
@@ -143,7 +143,7 @@ int launch_gather_rows(const void* emb, int dtype_store, int64_t n, int d, int d
     gather_rows_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(emb), n, d,
                                                                   d_pad, row_offset, rows, m, out);
   }
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 

@@ -114,7 +114,7 @@ int launch_metrics(const int64_t* retrieved, const int32_t* ret_count, int q, in
   if (k < 1) return fail(MMR_EINVAL, "metrics: k must be >= 1 (the reference divides by k)");
   metrics_kernel<<<(q + 3) / 4, 128, 0, stream>>>(retrieved, ret_count, q, k_ret, rel_indptr, rel_sorted,
                                                   rel_list_len, k, log2_tbl, out);
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 
@@ -126,7 +126,7 @@ int launch_label_relevance(const uint64_t* q_masks, int64_t nq, const uint64_t* 
   if (blocks > 148 * 16) blocks = 148 * 16;
   label_relevance_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(q_masks, nq, g_masks, ng, label_words,
                                                                        exclude_self, out);
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 

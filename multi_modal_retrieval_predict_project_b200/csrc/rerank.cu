@@ -220,7 +220,7 @@ int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pa
         static_cast<const float*>(emb), n, d_pad, row_offset, label_masks, label_words, kg, d_kg, n_rec, q_emb,
         cand_emb, cand_rows, q_rec, cand_rec, cand_count, k, d, out_raw, owned);
   }
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 
@@ -234,7 +234,7 @@ int launch_rerank_combine(const double* raw, const int32_t* cand_count, int b, i
   }
   rerank_combine_kernel<<<b, 256, smem, stream>>>(raw, cand_count, k, alpha, beta, gamma, topk, out_order,
                                                   out_scores);
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 

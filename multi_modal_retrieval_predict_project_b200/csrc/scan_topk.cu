@@ -183,7 +183,7 @@ int launch_one(const T* emb, const float* inv_norm, int64_t n, int d_pad, const 
   dim3 grid(plan.n_parts, (b + QB - 1) / QB);
   kern<<<grid, plan.warps * 32, plan.smem, stream>>>(emb, inv_norm, n, d_pad, q, q_inv, b, k, plan.kp, excl,
                                                      partial);
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 

@@ -121,7 +121,7 @@ int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_o
   auto kern = select_topk_kernel<Source>;
   MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<b, threads, smem, stream>>>(src, k_out, sz, keep, row_offset, out_scores, out_rows, out_src);
-  MMR_CUDA_TRY(cudaGetLastError());
+  MMR_LAUNCHED();
   return MMR_OK;
 }
 

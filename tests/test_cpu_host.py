@@ -22,7 +22,7 @@ def lib():
 def test_library_exports_every_declared_symbol(lib):
     from multi_modal_retrieval_predict_project_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "mmr_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(mmr_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(mmr_\w+)\s*\(", hdr, flags=re.M))
     assert len(declared) >= 16
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
