@@ -124,7 +124,18 @@ int stage_in(const void* src, size_t bytes, DeviceBuf& buf, cudaStream_t stream,
 
 namespace {
 
+// Device validation is cached per ordinal: cudaGetDeviceProperties costs milliseconds and the
+// handle-less entry points (merge, rerank, metrics) run once per query batch.
 int check_device(int device, int* num_sms) {
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cached_sms[kMaxDev];  // 0 = unknown, > 0 = validated sm_100 device
+  if (device >= 0 && device < kMaxDev) {
+    const int c = cached_sms[device].load(std::memory_order_acquire);
+    if (c > 0) {
+      if (num_sms != nullptr) *num_sms = c;
+      return MMR_OK;
+    }
+  }
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -132,13 +143,16 @@ int check_device(int device, int* num_sms) {
     return fail(MMR_ENODEV, "no CUDA device available: libmmr_b200 has no CPU fallback");
   }
   if (device < 0 || device >= count) return fail(MMR_EINVAL, "invalid device ordinal " + std::to_string(device));
-  cudaDeviceProp prop;
-  MMR_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
-    return fail(MMR_ENODEV, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) +
-                                std::to_string(prop.minor) + "; libmmr_b200 is built for sm_100a only");
+  int major = 0, minor = 0, sms = 0;
+  MMR_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  MMR_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  MMR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (major != 10) {
+    return fail(MMR_ENODEV, "device " + std::to_string(device) + " is sm_" + std::to_string(major) +
+                                std::to_string(minor) + "; libmmr_b200 is built for sm_100a only");
   }
-  if (num_sms != nullptr) *num_sms = prop.multiProcessorCount;
+  if (device < kMaxDev) cached_sms[device].store(sms, std::memory_order_release);
+  if (num_sms != nullptr) *num_sms = sms;
   return MMR_OK;
 }
 

@@ -235,6 +235,33 @@ __device__ __forceinline__ float warp_compact_dispatch(uint2* buf, int cnt, int 
   return warp_compact_generic(buf, cnt, k, lane, nullptr);
 }
 
+// Slow path of the epilogue for one score t = acc * inv_norm(g), branch-free: if t beats the
+// (conservative) pre-threshold, append {t * inv_norm(q), col} at the cursor and advance it.
+// Everything after the compare is predicated -- no BSSY/BRA per score (a divergent branch per
+// score made the first version of this kernel epilogue-bound at 5x the MMA time).
+__device__ __forceinline__ void score_step(uint2*& ptr, float t, float tau_pre, float qinv, uint32_t col) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .f32 s;\n\t"
+      "setp.gt.f32 p, %1, %2;\n\t"
+      "@p mul.f32 s, %1, %3;\n\t"
+      "@p st.global.v2.b32 [%0], {s, %4};\n\t"
+      "@p add.u64 %0, %0, 8;\n\t"
+      "}"
+      : "+l"(ptr)
+      : "f"(t), "f"(tau_pre), "f"(qinv), "r"(col)
+      : "memory");
+}
+
+// Threshold on t = acc * inv_norm(g) that never rejects a score whose final value
+// fl(t * qinv) exceeds tau: tau / qinv rounded down, then one more part in 2^22 below.  False
+// positives (a few ulps) are harmless -- compaction orders by the exact final key.
+__device__ __forceinline__ float pre_threshold(float tau, float qinv) {
+  const float r = __fdiv_rd(tau, qinv);  // qinv == 0: -inf stays -inf, 0/0 = NaN => nothing passes (all ties lose)
+  return r > 0.f ? __fmul_rd(r, 1.0f - 0x1p-22f) : __fmul_rd(r, 1.0f + 0x1p-22f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -342,11 +369,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int q = m_tile * kBlockM + row_in_tile;
     const bool q_ok = q < b;
     const float qinv = q_ok ? q_inv[q] : 0.f;
-    uint2* buf = cand + (static_cast<int64_t>(q_ok ? q : 0) * n_parts + part) * cap;
-    int cnt = 0;
-    float tau = q_ok ? -INFINITY : INFINITY;
-    const int epi_tid = threadIdx.x - 64;  // 0..127
+    uint2* const buf = cand + (static_cast<int64_t>(q_ok ? q : 0) * n_parts + part) * cap;
+    uint2* ptr = buf;                       // append cursor (cnt = ptr - buf)
+    float tau = q_ok ? -INFINITY : INFINITY;  // strict threshold on the FINAL score
+    float tau_pre = tau;                    // conservative threshold on acc * inv_norm(g) (see pre_threshold)
+    const int epi_tid = threadIdx.x - 64;   // 0..127
     const int64_t range_end = min(static_cast<int64_t>(tile_end) * kBlockN, n);
+    const uint32_t full_bytes = static_cast<uint32_t>(cap - 32) * 8u;
 
     for (int t = 0; t < num_tiles; ++t) {
       const int acc = t & 1;
@@ -361,38 +390,48 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(&aux->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
+      const uint32_t ginv_s = smem_u32(&aux->ginv[acc][0]);
 #pragma unroll 1
       for (int c = 0; c < kBlockN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
-        const float4* gi4 = reinterpret_cast<const float4*>(&aux->ginv[acc][c * 32]);
+        // fast path: t_j = acc_j * inv_norm(g_j) and the chunk maximum (NaN = out-of-range column,
+        // ignored by fmaxf); almost every chunk ends here once tau has tightened
+        float t[32];
+        float m = -INFINITY;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 gi = gi4[j4];
-          const float gs[4] = {gi.x, gi.y, gi.z, gi.w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = j4 * 4 + jj;
-            const float s = (__uint_as_float(v[j]) * gs[jj]) * qinv;
-            if (s > tau) {
-              buf[cnt] = make_uint2(__float_as_uint(s), static_cast<uint32_t>(n0 + c * 32 + j));
-              ++cnt;
-            }
-          }
+          float g0, g1, g2, g3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3)
+                       : "r"(ginv_s + static_cast<uint32_t>((c * 32 + j4 * 4) * 4)));
+          t[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) * g0;
+          t[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) * g1;
+          t[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) * g2;
+          t[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) * g3;
+          m = fmaxf(m, fmaxf(fmaxf(t[j4 * 4 + 0], t[j4 * 4 + 1]), fmaxf(t[j4 * 4 + 2], t[j4 * 4 + 3])));
         }
-        // make room for the next 32 columns: compact every query of this warp whose buffer is nearly full
-        uint32_t need = __ballot_sync(0xffffffffu, cnt > cap - 32);
-        while (need != 0u) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1u;
-          uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
-          const int scnt = __shfl_sync(0xffffffffu, cnt, src);
-          __syncwarp();
-          const float new_tau = warp_compact_dispatch(sbuf, scnt, k, cap, lane);
-          if (lane == src) {
-            cnt = k;
-            tau = new_tau;
+        if (__any_sync(0xffffffffu, m > tau_pre)) {  // warp-uniform
+          const uint32_t colbase = static_cast<uint32_t>(n0) + static_cast<uint32_t>(c * 32);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) score_step(ptr, t[j], tau_pre, qinv, colbase + j);
+          // make room for the next 32 columns: compact every query of this warp whose buffer is nearly full
+          const uint32_t used =
+              static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ptr) - reinterpret_cast<uintptr_t>(buf));
+          uint32_t need = __ballot_sync(0xffffffffu, used > full_bytes);
+          while (need != 0u) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1u;
+            uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
+            const int scnt = static_cast<int>(__shfl_sync(0xffffffffu, used, src) >> 3);
+            __syncwarp();
+            const float new_tau = warp_compact_dispatch(sbuf, scnt, k, cap, lane);
+            if (lane == src) {
+              ptr = buf + k;
+              tau = new_tau;
+              tau_pre = pre_threshold(new_tau, qinv);
+            }
           }
         }
       }
@@ -402,6 +441,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     // final exact top-k per query so that select.cu merges short lists
     {
+      int cnt = static_cast<int>(ptr - buf);
       uint32_t need = __ballot_sync(0xffffffffu, q_ok && cnt > k);
       while (need != 0u) {
         const int src = __ffs(need) - 1;
