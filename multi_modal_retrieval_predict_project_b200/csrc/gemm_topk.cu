@@ -34,25 +34,47 @@ constexpr int kBlockM = 128;          // queries per CTA tile (TMEM lanes)
 constexpr int kBlockN = 256;          // gallery rows per accumulator stage (UMMA N)
 constexpr int kBlockK = 64;           // bf16 elements per smem chunk row = 128 B (swizzle span)
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kBlockN;  // 512
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kMaxSmemOptin = 232448;             // 227 KiB per CTA on sm_100
 constexpr int kNumThreads = 192;                 // 6 warps
 constexpr int kEpiThreads = 128;
 
 struct __align__(16) SmemAux {
   float ginv[kAccStages][kBlockN];  // first: read as float4
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t q_full;   // resident-Q variant: all query chunks have landed
   uint64_t tmem_full[kAccStages];
   uint64_t tmem_empty[kAccStages];
   uint32_t tmem_base;
   uint32_t pad;
 };
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + static_cast<size_t>(kStages) * kStageBytes + sizeof(SmemAux);
+// Shared-memory plan.  kResident (d_pad <= 512): the 128-query tile stays in shared memory for
+// the whole CTA (num_kc x 16 KiB) and only gallery chunks stream through the stage ring, which
+// removes a third of the L2->SM and TMA->smem traffic.  Otherwise both operands stream per chunk.
+struct SmemPlan {
+  bool resident;
+  int num_stages;
+  int stage_bytes;
+  int q_bytes;
+  size_t total;
+};
+inline SmemPlan plan_smem(int d_pad) {
+  SmemPlan p;
+  const int num_kc = d_pad / kBlockK;
+  p.resident = static_cast<size_t>(num_kc) * kABytes + 2 * static_cast<size_t>(kBBytes) + sizeof(SmemAux) <=
+               static_cast<size_t>(kMaxSmemOptin);
+  p.q_bytes = p.resident ? num_kc * kABytes : 0;
+  p.stage_bytes = p.resident ? kBBytes : kABytes + kBBytes;
+  int st = static_cast<int>((kMaxSmemOptin - p.q_bytes - static_cast<int>(sizeof(SmemAux))) / p.stage_bytes);
+  p.num_stages = st > kMaxStages ? kMaxStages : st;
+  p.total = static_cast<size_t>(p.q_bytes) + static_cast<size_t>(p.num_stages) * p.stage_bytes + sizeof(SmemAux);
+  return p;
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -265,14 +287,21 @@ __device__ __forceinline__ float pre_threshold(float tau, float qinv) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+template <bool kResident>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                  const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
-                 int k, int cap, int m_tiles, int n_parts, int tiles_per_part, int tiles_total,
+                 int k, int cap, int m_tiles, int n_parts, int tiles_per_part, int tiles_total, int num_stages,
                  uint2* __restrict__ cand, int32_t* __restrict__ counts) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  SmemAux* aux = reinterpret_cast<SmemAux*>(smem + static_cast<size_t>(kStages) * kStageBytes);
+  // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; the declaration requests it and the
+  // kernel traps loudly if the runtime did not honour it (no slack bytes are budgeted).
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  const int num_kc = d_pad / kBlockK;
+  constexpr int kStageBytes = kResident ? kBBytes : kABytes + kBBytes;
+  uint8_t* const smem_q = smem_raw;                                             // resident query chunks
+  uint8_t* const smem = smem_raw + (kResident ? num_kc * kABytes : 0);          // stage ring
+  SmemAux* aux = reinterpret_cast<SmemAux*>(smem + static_cast<size_t>(num_stages) * kStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -281,15 +310,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int tile_begin = part * tiles_per_part;
   const int tile_end = min(tile_begin + tiles_per_part, tiles_total);
   const int num_tiles = tile_end - tile_begin;
-  const int num_kc = d_pad / kBlockK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_g);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < num_stages; ++s) {
       mbar_init(&aux->full[s], 1);
       mbar_init(&aux->empty[s], 1);
     }
+    mbar_init(&aux->q_full, 1);
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&aux->tmem_full[s], 1);
       mbar_init(&aux->tmem_empty[s], kEpiThreads / 32);
@@ -310,6 +339,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (kResident) {  // the query tile is loaded once and reused for every gallery tile
+        mbar_expect_tx(&aux->q_full, static_cast<uint32_t>(num_kc * kABytes));
+        for (int kc = 0; kc < num_kc; ++kc)
+          tma_load_2d(&tmap_q, &aux->q_full, smem_q + static_cast<size_t>(kc) * kABytes, kc * kBlockK,
+                      m_tile * kBlockM);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < num_tiles; ++t) {
@@ -317,11 +352,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int kc = 0; kc < num_kc; ++kc) {
           mbar_wait(&aux->empty[stage], phase ^ 1u);
           uint8_t* sa = smem + static_cast<size_t>(stage) * kStageBytes;
-          uint8_t* sb = sa + kABytes;
+          uint8_t* sb = kResident ? sa : sa + kABytes;
           mbar_expect_tx(&aux->full[stage], kStageBytes);
-          tma_load_2d(&tmap_q, &aux->full[stage], sa, kc * kBlockK, m_tile * kBlockM);
+          if (!kResident) tma_load_2d(&tmap_q, &aux->full[stage], sa, kc * kBlockK, m_tile * kBlockM);
           tma_load_2d(&tmap_g, &aux->full[stage], sb, kc * kBlockK, n0);
-          if (++stage == kStages) {
+          if (++stage == num_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -334,6 +369,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN);
       int stage = 0;
       uint32_t phase = 0;
+      if (kResident) mbar_wait(&aux->q_full, 0u);
       for (int t = 0; t < num_tiles; ++t) {
         const int acc = t & 1;
         const uint32_t acc_phase = (t >> 1) & 1u;
@@ -343,8 +379,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int kc = 0; kc < num_kc; ++kc) {
           mbar_wait(&aux->full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
+          const uint32_t sa = kResident ? smem_u32(smem_q + static_cast<size_t>(kc) * kABytes) : st;
+          const uint32_t sb = kResident ? st : st + kABytes;
           const uint64_t adesc = make_umma_desc(sa);
           const uint64_t bdesc = make_umma_desc(sb);
 #pragma unroll
@@ -354,7 +391,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                      (kc | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&aux->empty[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == kStages) {
+          if (++stage == num_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -546,18 +583,15 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   CUtensorMap tmap_q, tmap_g;
   MMR_TRY(make_tmap(&tmap_q, q_bf16, b, d_pad, kBlockM));
   MMR_TRY(make_tmap(&tmap_g, emb_bf16, n, d_pad, kBlockN));
-  static bool attr_set = false;
-  if (!attr_set) {
-    MMR_CUDA_TRY(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(kSmemBytes)));
-    attr_set = true;
-  }
+  const SmemPlan sp = plan_smem(d_pad);
+  if (sp.num_stages < 2) return fail(MMR_EUNSUP, "gemm: embedding dimension too large for the shared-memory plan");
   const int tiles_total = static_cast<int>((n + kBlockN - 1) / kBlockN);
   const int grid = plan.m_tiles * plan.n_parts;
-  gemm_topk_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k,
-                                                              plan.cap, plan.m_tiles, plan.n_parts,
-                                                              plan.ctas_per_mtile, tiles_total,
-                                                              reinterpret_cast<uint2*>(cand), counts);
+  auto kern = sp.resident ? gemm_topk_kernel<true> : gemm_topk_kernel<false>;
+  MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sp.total)));
+  kern<<<grid, kNumThreads, sp.total, stream>>>(tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap,
+                                                plan.m_tiles, plan.n_parts, plan.ctas_per_mtile, tiles_total,
+                                                sp.num_stages, reinterpret_cast<uint2*>(cand), counts);
   MMR_LAUNCHED();
   return MMR_OK;
 }

@@ -193,3 +193,35 @@ def test_merge_topk_matches_single_shard(algo):
     assert np.array_equal(mr.cpu().numpy(), rows) and np.array_equal(ms.cpu().numpy(), scores)
     flat_r = torch.stack(parts_r).permute(1, 0, 2).reshape(37, -1)
     assert torch.equal(torch.gather(flat_r, 1, src.long()), mr)
+
+
+@pytest.mark.parametrize("n,d,b,k", [(3000, 40, 20, 10), (5000, 100, 130, 33), (6000, 1024, 40, 100), (2000, 768, 5, 200)])
+def test_gemm_other_dims(n, d, b, k):
+    """GEMM path beyond the headline shape: padded D, the streamed-Q variant (D = 1024 does not fit the
+    resident-Q shared-memory plan), K > 128 (larger candidate buffers), multiple query tiles."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=81))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=82))
+    eng = _engine(g, dtype="bfloat16")
+    rows, scores = eng.search(q, k, algo="gemm")
+    want_rows, want_scores = osr.exact_topk(q, g, k)
+    _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+
+
+def test_gemm_duplicates_and_zero_rows():
+    """Exact-score ties (duplicated gallery rows, reference Trainner/train.py:438-454 samples with
+    replacement) resolve to ascending row id; zero rows / zero queries score exactly 0."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(4096, 128, seed=91))
+    g[100:400] = g[7]            # 300 copies of one row: more ties than k
+    g[1000] = 0.0
+    q = osr.to_bf16_round(synth.make_embeddings(17, 128, seed=92))
+    q[3] = g[7]
+    q[5] = 0.0
+    eng = _engine(g, dtype="bfloat16")
+    for algo in ("scan", "gemm"):
+        rows, scores = eng.search(q, 50, algo=algo)
+        assert rows[3, 0] == 7 and np.array_equal(rows[3, 1:50], np.arange(100, 149)), algo
+        assert np.all(scores[5] == 0.0) and np.array_equal(rows[5], np.arange(50)), algo
+        want_rows, want_scores = osr.exact_topk(q, g, 50)
+        _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
