@@ -4,6 +4,7 @@
 // kernel sequencing on the caller's stream.  No compute happens on the CPU and there is no CPU
 // fallback: every path ends in a kernel launch or an error code.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -25,7 +26,7 @@ struct mmr_index {
   bool owns_emb = true;
   float* inv_norm = nullptr;
   std::mutex mu;  // search is re-entrant per handle by serialising on the handle's workspaces
-  mmr::DeviceBuf q_in, q_store, q_f32, q_inv, scratch, excl_in, excl_local, partial, counts, out_scores, out_rows;
+  mmr::DeviceBuf q_in, q_store, q_f32, q_inv, scratch, excl_in, excl_local, partial, counts, tau_pub, out_scores, out_rows;
   // live kernel timing (mmr_index_profile)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_start, ev_stop;
@@ -45,6 +46,8 @@ namespace mmr {
 
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
+// MMR_B200_NO_TAU_SHARE=1 disables the cross-CTA threshold exchange of the GEMM path (A/B testing)
+static const bool g_share_tau = std::getenv("MMR_B200_NO_TAU_SHARE") == nullptr;
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
@@ -346,7 +349,7 @@ int mmr_index_destroy(mmr_index* ix) {
   if (ix->owns_emb && ix->emb) cudaFree(ix->emb);
   if (ix->inv_norm) cudaFree(ix->inv_norm);
   for (DeviceBuf* b : {&ix->q_in, &ix->q_store, &ix->q_f32, &ix->q_inv, &ix->scratch, &ix->excl_in, &ix->excl_local, &ix->partial,
-                       &ix->counts, &ix->out_scores, &ix->out_rows})
+                       &ix->counts, &ix->tau_pub, &ix->out_scores, &ix->out_rows})
     b->release();
   for (cudaEvent_t e : ix->ev_start) cudaEventDestroy(e);
   for (cudaEvent_t e : ix->ev_stop) cudaEventDestroy(e);
@@ -461,11 +464,13 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     MMR_TRY(plan_gemm(ix->n, ix->d_pad, b, k_eff, ix->num_sms, &gp));
     MMR_TRY(ix->partial.ensure(gp.cand_bytes));
     MMR_TRY(ix->counts.ensure(gp.count_bytes));
+    MMR_TRY(ix->tau_pub.ensure(gp.pub_bytes));
     if (ev0) MMR_CUDA_TRY(cudaEventRecord(ev0, stream));
     MMR_TRY(launch_gemm_topk(ix->emb, ix->inv_norm, ix->n, ix->d_pad, ix->q_store.p, ix->q_inv.as<float>(), b, k_eff,
-                             d_excl, gp, ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), stream));
+                             d_excl, gp, ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(),
+                             g_share_tau ? ix->tau_pub.as<uint32_t>() : nullptr, stream));
     if (ev1) MMR_CUDA_TRY(cudaEventRecord(ev1, stream));
-    MMR_TRY(launch_select_var(ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), b, gp.n_parts, gp.cap, k_eff, k,
+    MMR_TRY(launch_select_var(ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), b, gp.n_lists, gp.cap, k_eff, k,
                               ix->row_offset, d_excl, d_scores, d_rows, stream));
   } else {
     const float* q_f32 = nullptr;

@@ -6,24 +6,31 @@
 //
 //   scores[m, n] = sum_d Q[m, d] * G[n, d]      Q: (b, d_pad) bf16, G: (n, d_pad) bf16, both K-major
 //
-// CTA = (query tile of 128 rows) x (contiguous range of gallery tiles of 256 rows).  Warp roles:
-//   warp 0   TMA producer: cp.async.bulk.tensor 128B-swizzled [128 x 64] Q chunk + [256 x 64] G chunk
-//            per pipeline stage (4 stages x 48 KiB), mbarrier complete_tx.
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256,
-//            K=16), fp32 accumulators in TMEM, 2 accumulator stages x 256 columns; tcgen05.commit
-//            releases smem stages and publishes finished accumulators.
-//   warps 2-5 epilogue: thread <-> query row (TMEM lane).  tcgen05.ld 32 columns at a time,
-//            s = (acc * inv_norm[g]) * inv_norm[q], strict threshold test s > tau against the
-//            thread's running k-th best; survivors are appended to the query's candidate buffer in
-//            global memory (L2-resident, rarely written).  When a buffer fills, the warp
-//            cooperatively selects the exact top-k (bitwise radix descent on 64-bit keys held in
-//            registers), compacts the buffer and tightens tau.
-// Per (query, CTA) the gallery rows arrive in increasing order, so on an exact score tie the
-// earlier row is already buffered and the strict test implements "score desc, row asc".
-// select.cu merges the per-CTA lists.
+// CTA = (query tile of 128 rows) x (contiguous range of gallery tiles of 256 rows), 12 warps:
+//   warp 0    TMA producer: cp.async.bulk.tensor, 128B-swizzled [256 x 64] gallery chunks into a stage
+//             ring (mbarrier complete_tx).  For d_pad <= 512 the [128 x d_pad] query tile is loaded once
+//             and stays resident in shared memory; otherwise query chunks stream with the gallery.
+//   warp 1    MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
+//             fp32 accumulators in TMEM (2 stages x 256 columns); tcgen05.commit frees smem stages and
+//             publishes finished accumulators.  Warps 2-3 idle (they donate registers).
+//   warps 4-11 epilogue, two warpgroups: group g owns accumulator stage g, i.e. gallery tiles g, g+2, ...
+//             so each group has two MMA tile times per tile.  thread <-> query row (TMEM lane).
+//             tcgen05.ld 32 columns -> t = acc * inv_norm(g) -> chunk max; only if some lane's max beats
+//             its threshold does the warp run the (predicated, branch-free) append path.  Survivors go
+//             to the (query, part, group) candidate list in global memory (L2-resident, rarely written);
+//             when a list fills, the warp selects the exact top-k with a bitwise radix descent over
+//             64-bit keys held in registers, compacts the list and tightens the threshold.
+//   Registers are rebalanced with setmaxnreg (40 for warps 0-3, 232 for the epilogue).
+// Thresholds: per list, the score of its own k-th best (strict: gallery rows reach a list in
+// increasing order, so on an exact tie the earlier row is already there => "score desc, row asc");
+// across lists, every list publishes the score of its r-th best, r = ceil(k / n_lists): if every
+// list holds >= r candidates >= g = min over lists, the union holds >= k, so nothing below g can be
+// in the global top-k and all CTAs of the query tile prune with g.  select.cu merges the lists.
 //
 // Roofline: tensor-core bound, 2 * b * n * d_pad FLOP per launch.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -40,8 +47,11 @@ constexpr int kTmemCols = kAccStages * kBlockN;  // 512
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KiB
 constexpr int kMaxSmemOptin = 232448;             // 227 KiB per CTA on sm_100
-constexpr int kNumThreads = 192;                 // 6 warps
-constexpr int kEpiThreads = 128;
+constexpr int kEpiGroups = 2;                     // epilogue warpgroups (one per accumulator stage)
+constexpr int kEpiThreads = 128;                  // threads per epilogue warpgroup
+constexpr int kFirstEpiWarp = 4;
+constexpr int kNumThreads = 128 + kEpiGroups * kEpiThreads;  // 384
+constexpr int kRegsLow = 40, kRegsHigh = 232;     // 128*40 + 256*232 = 64512 <= 65536
 
 struct __align__(16) SmemAux {
   float ginv[kAccStages][kBlockN];  // first: read as float4
@@ -87,20 +97,26 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase
+// completes (or the hint expires) instead of re-issuing the poll every few cycles -- the producer
+// and MMA warps share their SM sub-partitions with epilogue warps and must not steal issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra.uni WAIT_DONE;\n\t"
       "bra.uni WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -166,18 +182,22 @@ __device__ __forceinline__ uint64_t entry_key(uint2 e) { return make_key(__uint_
 
 // ---------------------------------------------------------------------------------------------
 // Warp-cooperative exact top-k of one query's candidate buffer (cnt <= E*32 entries).
-// Returns the new strict threshold (score of the k-th best); the buffer front holds the k best.
+// The buffer front ends up holding the k best; returns the score of the k-th best (the new strict
+// local threshold) and, through *rth_score, the score of the r-th best (r <= k), which the CTA
+// publishes so that all CTAs scanning other gallery parts for the same query can prune with it.
 // ---------------------------------------------------------------------------------------------
-template <int E>
-__device__ __forceinline__ float warp_compact(uint2* buf, int cnt, int k, int lane) {
-  uint64_t key[E];
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int i = e * 32 + lane;
-    key[e] = (i < cnt) ? entry_key(buf[i]) : 0ull;
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other < v ? other : v;
   }
-  __syncwarp();
-  // largest T with count(key >= T) >= k, found MSB first; stop as soon as the count is exactly k
+  return v;
+}
+
+// largest-prefix threshold T with count(key >= T) == rank (keys are distinct), found MSB first
+template <int E>
+__device__ __forceinline__ uint64_t warp_rank_threshold(const uint64_t (&key)[E], int rank) {
   uint64_t prefix = 0;
   for (int bit = 63; bit >= 0; --bit) {
     const uint64_t cand = prefix | (1ull << bit);
@@ -185,17 +205,30 @@ __device__ __forceinline__ float warp_compact(uint2* buf, int cnt, int k, int la
 #pragma unroll
     for (int e = 0; e < E; ++e) c += (key[e] >= cand) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= k) {
+    if (c >= rank) {
       prefix = cand;
-      if (c == k) break;
+      if (c == rank) break;
     }
   }
-  // keep key >= prefix (exactly k of them when cnt >= k), compacting in place
+  return prefix;
+}
+
+template <int E>
+__device__ __forceinline__ float warp_compact(uint2* buf, int cnt, int k, int r, int lane, float* rth_score) {
+  uint64_t key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    key[e] = (i < cnt) ? entry_key(buf[i]) : 0ull;
+  }
+  __syncwarp();
+  const uint64_t tk = warp_rank_threshold<E>(key, k);
+  // keep key >= tk (exactly k of them when cnt >= k), compacting in place
   uint64_t kmin = ~0ull;
   int base = 0;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    const bool keep = key[e] >= prefix && key[e] != 0ull;
+    const bool keep = key[e] >= tk && key[e] != 0ull;
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int pos = base + __popc(m & ((1u << lane) - 1u));
@@ -204,27 +237,44 @@ __device__ __forceinline__ float warp_compact(uint2* buf, int cnt, int k, int la
     }
     base += __popc(m);
   }
+  kmin = warp_min_u64(kmin);
+  if (rth_score != nullptr) {
+    const uint64_t tr = (r >= k) ? tk : warp_rank_threshold<E>(key, r);
+    uint64_t rmin = ~0ull;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const uint64_t other = __shfl_xor_sync(0xffffffffu, kmin, o);
-    kmin = other < kmin ? other : kmin;
+    for (int e = 0; e < E; ++e) rmin = (key[e] >= tr && key[e] < rmin) ? key[e] : rmin;
+    *rth_score = key_score(warp_min_u64(rmin));
   }
   __syncwarp();
   return key_score(kmin);
 }
 
 // generic version for large k: keys are re-read from the (L2-resident) buffer every pass
-__device__ __noinline__ float warp_compact_generic(uint2* buf, int cnt, int k, int lane, uint2* scratch) {
+__device__ __noinline__ uint64_t warp_rank_threshold_generic(const uint2* buf, int cnt, int rank, int lane) {
   uint64_t prefix = 0;
   for (int bit = 63; bit >= 0; --bit) {
     const uint64_t cand = prefix | (1ull << bit);
     int c = 0;
     for (int i = lane; i < cnt; i += 32) c += (entry_key(buf[i]) >= cand) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= k) {
+    if (c >= rank) {
       prefix = cand;
-      if (c == k) break;
+      if (c == rank) break;
     }
+  }
+  return prefix;
+}
+
+__device__ __noinline__ float warp_compact_generic(uint2* buf, int cnt, int k, int r, int lane, float* rth_score) {
+  const uint64_t tk = warp_rank_threshold_generic(buf, cnt, k, lane);
+  if (rth_score != nullptr) {
+    const uint64_t tr = (r >= k) ? tk : warp_rank_threshold_generic(buf, cnt, r, lane);
+    uint64_t rmin = ~0ull;
+    for (int i = lane; i < cnt; i += 32) {
+      const uint64_t key = entry_key(buf[i]);
+      rmin = (key >= tr && key < rmin) ? key : rmin;
+    }
+    *rth_score = key_score(warp_min_u64(rmin));
   }
   // stable in-place compaction: a kept element never moves to a higher index, and rounds proceed
   // in increasing index order, so reads of later rounds are never clobbered
@@ -234,7 +284,7 @@ __device__ __noinline__ float warp_compact_generic(uint2* buf, int cnt, int k, i
     const int i = i0 + lane;
     const uint2 e = (i < cnt) ? buf[i] : make_uint2(0u, 0u);
     const uint64_t key = (i < cnt) ? entry_key(e) : 0ull;
-    const bool keep = key >= prefix && key != 0ull;
+    const bool keep = key >= tk && key != 0ull;
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
     __syncwarp();
     if (keep) {
@@ -244,17 +294,14 @@ __device__ __noinline__ float warp_compact_generic(uint2* buf, int cnt, int k, i
     base += __popc(m);
     __syncwarp();
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const uint64_t other = __shfl_xor_sync(0xffffffffu, kmin, o);
-    kmin = other < kmin ? other : kmin;
-  }
-  return key_score(kmin);
+  return key_score(warp_min_u64(kmin));
 }
 
-__device__ __forceinline__ float warp_compact_dispatch(uint2* buf, int cnt, int k, int cap, int lane) {
-  if (cap == 512) return warp_compact<16>(buf, cnt, k, lane);
-  if (cap == 1024) return warp_compact<32>(buf, cnt, k, lane);
-  return warp_compact_generic(buf, cnt, k, lane, nullptr);
+__device__ __forceinline__ float warp_compact_dispatch(uint2* buf, int cnt, int k, int r, int cap, int lane,
+                                                       float* rth_score) {
+  if (cap == 512) return warp_compact<16>(buf, cnt, k, r, lane, rth_score);
+  if (cap == 1024) return warp_compact<32>(buf, cnt, k, r, lane, rth_score);
+  return warp_compact_generic(buf, cnt, k, r, lane, rth_score);
 }
 
 // Slow path of the epilogue for one score t = acc * inv_norm(g), branch-free: if t beats the
@@ -292,7 +339,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                  const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
                  int k, int cap, int m_tiles, int n_parts, int tiles_per_part, int tiles_total, int num_stages,
-                 uint2* __restrict__ cand, int32_t* __restrict__ counts) {
+                 int pub_rank, int refresh_tiles, int debug_flags, uint2* __restrict__ cand,
+                 int32_t* __restrict__ counts, uint32_t* __restrict__ tau_pub) {
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; the declaration requests it and the
   // kernel traps loudly if the runtime did not honour it (no slack bytes are budgeted).
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -305,8 +353,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x % m_tiles;
-  const int part = blockIdx.x / m_tiles;
+  // part is the fastest index: the CTAs scanning different gallery parts for the SAME query tile
+  // run in the same wave and exchange pruning thresholds through tau_pub
+  const int m_tile = blockIdx.x / n_parts;
+  const int part = blockIdx.x % n_parts;
   const int tile_begin = part * tiles_per_part;
   const int tile_end = min(tile_begin + tiles_per_part, tiles_total);
   const int num_tiles = tile_end - tile_begin;
@@ -336,106 +386,137 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = aux->tmem_base;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (kResident) {  // the query tile is loaded once and reused for every gallery tile
-        mbar_expect_tx(&aux->q_full, static_cast<uint32_t>(num_kc * kABytes));
-        for (int kc = 0; kc < num_kc; ++kc)
-          tma_load_2d(&tmap_q, &aux->q_full, smem_q + static_cast<size_t>(kc) * kABytes, kc * kBlockK,
-                      m_tile * kBlockM);
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < num_tiles; ++t) {
-        const int n0 = (tile_begin + t) * kBlockN;
-        for (int kc = 0; kc < num_kc; ++kc) {
-          mbar_wait(&aux->empty[stage], phase ^ 1u);
-          uint8_t* sa = smem + static_cast<size_t>(stage) * kStageBytes;
-          uint8_t* sb = kResident ? sa : sa + kABytes;
-          mbar_expect_tx(&aux->full[stage], kStageBytes);
-          if (!kResident) tma_load_2d(&tmap_q, &aux->full[stage], sa, kc * kBlockK, m_tile * kBlockM);
-          tma_load_2d(&tmap_g, &aux->full[stage], sb, kc * kBlockK, n0);
-          if (++stage == num_stages) {
-            stage = 0;
-            phase ^= 1u;
+  if (warp < kFirstEpiWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLow));
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        if (kResident) {  // the query tile is loaded once and reused for every gallery tile
+          mbar_expect_tx(&aux->q_full, static_cast<uint32_t>(num_kc * kABytes));
+          for (int kc = 0; kc < num_kc; ++kc)
+            tma_load_2d(&tmap_q, &aux->q_full, smem_q + static_cast<size_t>(kc) * kABytes, kc * kBlockK,
+                        m_tile * kBlockM);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < num_tiles; ++t) {
+          const int n0 = (tile_begin + t) * kBlockN;
+          for (int kc = 0; kc < num_kc; ++kc) {
+            mbar_wait(&aux->empty[stage], phase ^ 1u);
+            uint8_t* sa = smem + static_cast<size_t>(stage) * kStageBytes;
+            uint8_t* sb = kResident ? sa : sa + kABytes;
+            mbar_expect_tx(&aux->full[stage], kStageBytes);
+            if (!kResident) tma_load_2d(&tmap_q, &aux->full[stage], sa, kc * kBlockK, m_tile * kBlockM);
+            tma_load_2d(&tmap_g, &aux->full[stage], sb, kc * kBlockK, n0);
+            if (++stage == num_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN);
-      int stage = 0;
-      uint32_t phase = 0;
-      if (kResident) mbar_wait(&aux->q_full, 0u);
-      for (int t = 0; t < num_tiles; ++t) {
-        const int acc = t & 1;
-        const uint32_t acc_phase = (t >> 1) & 1u;
-        mbar_wait(&aux->tmem_empty[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBlockN);
-        for (int kc = 0; kc < num_kc; ++kc) {
-          mbar_wait(&aux->full[stage], phase);
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN);
+        int stage = 0;
+        uint32_t phase = 0;
+        if (kResident) mbar_wait(&aux->q_full, 0u);
+        for (int t = 0; t < num_tiles; ++t) {
+          const int acc = t & 1;
+          const uint32_t acc_phase = (t >> 1) & 1u;
+          mbar_wait(&aux->tmem_empty[acc], acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
-          const uint32_t sa = kResident ? smem_u32(smem_q + static_cast<size_t>(kc) * kABytes) : st;
-          const uint32_t sb = kResident ? st : st + kABytes;
-          const uint64_t adesc = make_umma_desc(sa);
-          const uint64_t bdesc = make_umma_desc(sb);
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBlockN);
+          for (int kc = 0; kc < num_kc; ++kc) {
+            mbar_wait(&aux->full[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
+            const uint32_t sa = kResident ? smem_u32(smem_q + static_cast<size_t>(kc) * kABytes) : st;
+            const uint32_t sb = kResident ? st : st + kABytes;
+            const uint64_t adesc = make_umma_desc(sa);
+            const uint64_t bdesc = make_umma_desc(sb);
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
-            umma_f16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc + static_cast<uint64_t>(kk * 2), idesc,
-                     (kc | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
+              umma_f16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc + static_cast<uint64_t>(kk * 2), idesc,
+                       (kc | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&aux->empty[stage]);  // frees the smem stage when these MMAs retire
+            if (++stage == num_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
-          umma_commit(&aux->empty[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == num_stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          umma_commit(&aux->tmem_full[acc]);  // accumulator complete
         }
-        umma_commit(&aux->tmem_full[acc]);  // accumulator complete
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsHigh));
     // ===================== epilogue: scale + threshold + top-k =====================
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row_in_tile = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const int group = (warp - kFirstEpiWarp) >> 2;  // == accumulator stage this warpgroup drains
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;    // query row within the tile == TMEM lane
     const int q = m_tile * kBlockM + row_in_tile;
+    const int b_pad = m_tiles * kBlockM;
+    const int n_lists = n_parts * kEpiGroups;
+    const int list = part * kEpiGroups + group;
     const bool q_ok = q < b;
     const float qinv = q_ok ? q_inv[q] : 0.f;
-    uint2* const buf = cand + (static_cast<int64_t>(q_ok ? q : 0) * n_parts + part) * cap;
-    uint2* ptr = buf;                       // append cursor (cnt = ptr - buf)
-    float tau = q_ok ? -INFINITY : INFINITY;  // strict threshold on the FINAL score
-    float tau_pre = tau;                    // conservative threshold on acc * inv_norm(g) (see pre_threshold)
-    const int epi_tid = threadIdx.x - 64;   // 0..127
+    uint2* const buf = cand + (static_cast<int64_t>(q_ok ? q : 0) * n_lists + list) * cap;
+    uint2* ptr = buf;                                // append cursor (count = ptr - buf)
+    float tau_local = q_ok ? -INFINITY : INFINITY;   // pre-threshold from this list's own k-th best (strict)
+    float tau_pre = tau_local;                       // effective conservative threshold on acc * inv_norm(g)
+    const int epi_tid = threadIdx.x - (kFirstEpiWarp * 32 + group * kEpiThreads);  // 0..127
     const int64_t range_end = min(static_cast<int64_t>(tile_end) * kBlockN, n);
     const uint32_t full_bytes = static_cast<uint32_t>(cap - 32) * 8u;
+    const uint32_t nan_bits = 0x7FC00000u;           // marks gallery rows outside the range: never a hit
+    const int bar_id = 1 + group;                    // named barrier of this warpgroup
+    float* const ginv = aux->ginv[group];
+    const uint32_t ginv_s = smem_u32(ginv);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(group * kBlockN);
 
-    for (int t = 0; t < num_tiles; ++t) {
-      const int acc = t & 1;
+    // inverse norms of this group's first tile; later tiles are prefetched one tile (of the group) ahead
+    float gnext0 = __uint_as_float(nan_bits), gnext1 = gnext0;
+    if (group < num_tiles) {
+      const int64_t r0 = static_cast<int64_t>(tile_begin + group) * kBlockN + epi_tid, r1 = r0 + kEpiThreads;
+      if (r0 < range_end) gnext0 = __ldg(inv_norm + r0);
+      if (r1 < range_end) gnext1 = __ldg(inv_norm + r1);
+    }
+
+    for (int t = group; t < num_tiles; t += kEpiGroups) {
       const uint32_t acc_phase = (t >> 1) & 1u;
       const int64_t n0 = static_cast<int64_t>(tile_begin + t) * kBlockN;
-      // stage this tile's gallery inverse norms (NaN marks rows outside the range: never a hit)
-      for (int i = epi_tid; i < kBlockN; i += kEpiThreads) {
-        const int64_t r = n0 + i;
-        aux->ginv[acc][i] = (r < range_end) ? __ldg(inv_norm + r) : __int_as_float(0x7FC00000);
+      ginv[epi_tid] = gnext0;
+      ginv[epi_tid + kEpiThreads] = gnext1;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // ginv of this tile is complete
+      gnext0 = gnext1 = __uint_as_float(nan_bits);
+      if (t + kEpiGroups < num_tiles) {
+        const int64_t r0 = n0 + kEpiGroups * kBlockN + epi_tid, r1 = r0 + kEpiThreads;
+        if (r0 < range_end) gnext0 = __ldg(inv_norm + r0);
+        if (r1 < range_end) gnext1 = __ldg(inv_norm + r1);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&aux->tmem_full[acc], acc_phase);
+      // refresh the cross-CTA pruning bound (0 = "not published yet" => no pruning); purely
+      // advisory and monotone, so stale reads are safe
+      if (tau_pub != nullptr && ((t >> 1) % refresh_tiles) == 0 && t >= kEpiGroups && q_ok) {
+        uint32_t g = 0xFFFFFFFFu;
+        for (int p = 0; p < n_lists; ++p) {
+          const uint32_t v = __ldcg(tau_pub + static_cast<int64_t>(p) * b_pad + q);
+          g = v < g ? v : g;
+        }
+        if (g != 0u) tau_pre = fmaxf(tau_local, pre_threshold(ordered_to_f32(g), qinv));
+      }
+      mbar_wait(&aux->tmem_full[group], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
-      const uint32_t ginv_s = smem_u32(&aux->ginv[acc][0]);
 #pragma unroll 1
-      for (int c = 0; c < kBlockN / 32; ++c) {
+      for (int c = 0; c < ((debug_flags & 1) ? 0 : kBlockN / 32); ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
         // fast path: t_j = acc_j * inv_norm(g_j) and the chunk maximum (NaN = out-of-range column,
-        // ignored by fmaxf); almost every chunk ends here once tau has tightened
-        float t[32];
+        // ignored by fmaxf); almost every chunk ends here once the threshold has tightened
+        float tv[32];
         float m = -INFINITY;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -443,17 +524,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3)
                        : "r"(ginv_s + static_cast<uint32_t>((c * 32 + j4 * 4) * 4)));
-          t[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) * g0;
-          t[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) * g1;
-          t[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) * g2;
-          t[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) * g3;
-          m = fmaxf(m, fmaxf(fmaxf(t[j4 * 4 + 0], t[j4 * 4 + 1]), fmaxf(t[j4 * 4 + 2], t[j4 * 4 + 3])));
+          tv[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) * g0;
+          tv[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) * g1;
+          tv[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) * g2;
+          tv[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) * g3;
+          m = fmaxf(m, fmaxf(fmaxf(tv[j4 * 4 + 0], tv[j4 * 4 + 1]), fmaxf(tv[j4 * 4 + 2], tv[j4 * 4 + 3])));
         }
         if (__any_sync(0xffffffffu, m > tau_pre)) {  // warp-uniform
           const uint32_t colbase = static_cast<uint32_t>(n0) + static_cast<uint32_t>(c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) score_step(ptr, t[j], tau_pre, qinv, colbase + j);
-          // make room for the next 32 columns: compact every query of this warp whose buffer is nearly full
+          for (int j = 0; j < 32; ++j) score_step(ptr, tv[j], tau_pre, qinv, colbase + j);
+          // make room for the next 32 columns: compact every list of this warp that is nearly full
           const uint32_t used =
               static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ptr) - reinterpret_cast<uintptr_t>(buf));
           uint32_t need = __ballot_sync(0xffffffffu, used > full_bytes);
@@ -463,20 +544,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
             const int scnt = static_cast<int>(__shfl_sync(0xffffffffu, used, src) >> 3);
             __syncwarp();
-            const float new_tau = warp_compact_dispatch(sbuf, scnt, k, cap, lane);
+            float rth = 0.f;
+            const float new_tau = warp_compact_dispatch(sbuf, scnt, k, pub_rank, cap, lane,
+                                                        tau_pub != nullptr ? &rth : nullptr);
             if (lane == src) {
               ptr = buf + k;
-              tau = new_tau;
-              tau_pre = pre_threshold(new_tau, qinv);
+              tau_local = pre_threshold(new_tau, qinv);
+              tau_pre = fmaxf(tau_pre, tau_local);
+              if (tau_pub != nullptr) __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
             }
           }
         }
       }
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&aux->tmem_empty[acc]);
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // all 4 warps are done with TMEM stage + ginv
+      if (epi_tid == 0) mbar_arrive_n(&aux->tmem_empty[group], kEpiThreads / 32);
     }
-    // final exact top-k per query so that select.cu merges short lists
+    // final exact top-k per list so that select.cu merges short lists
     {
       int cnt = static_cast<int>(ptr - buf);
       uint32_t need = __ballot_sync(0xffffffffu, q_ok && cnt > k);
@@ -486,10 +570,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
         const int scnt = __shfl_sync(0xffffffffu, cnt, src);
         __syncwarp();
-        (void)warp_compact_dispatch(sbuf, scnt, k, cap, lane);
+        (void)warp_compact_dispatch(sbuf, scnt, k, k, cap, lane, nullptr);
         if (lane == src) cnt = k;
       }
-      if (q_ok) counts[static_cast<int64_t>(q) * n_parts + part] = cnt;
+      if (q_ok) counts[static_cast<int64_t>(q) * n_lists + list] = cnt;
     }
   }
 
@@ -570,16 +654,18 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
   if (k > 256) cap = 4096;
   plan->m_tiles = m_tiles;
   plan->n_parts = n_parts;
-  plan->ctas_per_mtile = tiles_per_part;  // (re-used field: tiles per part)
+  plan->n_lists = n_parts * kEpiGroups;
+  plan->tiles_per_part = tiles_per_part;
   plan->cap = cap;
-  plan->cand_bytes = static_cast<size_t>(b) * n_parts * cap * sizeof(uint2);
-  plan->count_bytes = static_cast<size_t>(b) * n_parts * sizeof(int32_t);
+  plan->cand_bytes = static_cast<size_t>(b) * plan->n_lists * cap * sizeof(uint2);
+  plan->count_bytes = static_cast<size_t>(b) * plan->n_lists * sizeof(int32_t);
+  plan->pub_bytes = static_cast<size_t>(m_tiles) * kBlockM * plan->n_lists * sizeof(uint32_t);
   return MMR_OK;
 }
 
 int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int d_pad, const void* q_bf16,
                      const float* q_inv, int b, int k, const int64_t* /*exclude_local: applied by select*/,
-                     const GemmPlan& plan, uint64_t* cand, int32_t* counts, cudaStream_t stream) {
+                     const GemmPlan& plan, uint64_t* cand, int32_t* counts, uint32_t* tau_pub, cudaStream_t stream) {
   CUtensorMap tmap_q, tmap_g;
   MMR_TRY(make_tmap(&tmap_q, q_bf16, b, d_pad, kBlockM));
   MMR_TRY(make_tmap(&tmap_g, emb_bf16, n, d_pad, kBlockN));
@@ -589,9 +675,19 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   const int grid = plan.m_tiles * plan.n_parts;
   auto kern = sp.resident ? gemm_topk_kernel<true> : gemm_topk_kernel<false>;
   MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sp.total)));
+  // threshold exchange: rank published per part and refresh period (in gallery tiles)
+  // MMR_B200_GEMM_DEBUG bit 0: skip the epilogue's score processing (results are garbage) to
+  // measure the TMA + MMA pipeline alone
+  static const int debug_flags = std::getenv("MMR_B200_GEMM_DEBUG") ? std::atoi(std::getenv("MMR_B200_GEMM_DEBUG")) : 0;
+  const int pub_rank = (k + plan.n_lists - 1) / plan.n_lists;
+  const int refresh = plan.n_lists <= 48 ? 1 : (plan.n_lists + 47) / 48;
+  if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
+  // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
+  MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));
   kern<<<grid, kNumThreads, sp.total, stream>>>(tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap,
-                                                plan.m_tiles, plan.n_parts, plan.ctas_per_mtile, tiles_total,
-                                                sp.num_stages, reinterpret_cast<uint2*>(cand), counts);
+                                                plan.m_tiles, plan.n_parts, plan.tiles_per_part, tiles_total,
+                                                sp.num_stages, pub_rank, refresh, debug_flags,
+                                                reinterpret_cast<uint2*>(cand), counts, tau_pub);
   MMR_LAUNCHED();
   return MMR_OK;
 }

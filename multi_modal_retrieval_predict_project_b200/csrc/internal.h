@@ -71,16 +71,19 @@ int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, in
 
 // gemm_topk.cu: tcgen05 GEMM + fused top-K (bf16 storage).
 struct GemmPlan {
-  int n_parts;          // partial lists per query
-  int cap;              // candidate capacity per (query, part)
+  int m_tiles;          // query tiles of 128
+  int n_parts;          // gallery parts (CTAs per query tile)
+  int n_lists;          // candidate lists per query (parts x epilogue warpgroups)
+  int tiles_per_part;   // gallery tiles of 256 rows per part
+  int cap;              // candidate capacity per list
   size_t cand_bytes;    // candidate buffer bytes
-  size_t count_bytes;   // per-(query, part) counts
-  int m_tiles, ctas_per_mtile;  // ctas_per_mtile holds the gallery tiles per part
+  size_t count_bytes;   // per-(query, list) counts
+  size_t pub_bytes;     // per-(list, query) published pruning thresholds
 };
 int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan);
 int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int d_pad, const void* q_bf16,
                      const float* q_inv, int b, int k, const int64_t* exclude_local, const GemmPlan& plan,
-                     uint64_t* cand, int32_t* counts, cudaStream_t stream);
+                     uint64_t* cand, int32_t* counts, uint32_t* tau_pub, cudaStream_t stream);
 int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int per_part,
                       int k_out, int64_t row_offset, const int64_t* exclude_local, float* out_scores,
                       int64_t* out_rows, cudaStream_t stream);
