@@ -338,7 +338,8 @@ template <bool kResident>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                  const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
-                 int k, int cap, int m_tiles, int n_parts, int tiles_per_part, int tiles_total, int num_stages,
+                 int k, int cap, int m_tiles, int m_group, int n_parts, int tiles_per_part, int tiles_total,
+                 int num_stages,
                  int pub_rank, int refresh_tiles, int debug_flags, uint2* __restrict__ cand,
                  int32_t* __restrict__ counts, uint32_t* __restrict__ tau_pub) {
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; the declaration requests it and the
@@ -353,10 +354,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // part is the fastest index: the CTAs scanning different gallery parts for the SAME query tile
-  // run in the same wave and exchange pruning thresholds through tau_pub
-  const int m_tile = blockIdx.x / n_parts;
-  const int part = blockIdx.x % n_parts;
+  // CTA order: waves of `m_group` query tiles x all gallery parts, query tile fastest.  All parts of a
+  // query tile are co-resident (they exchange pruning thresholds through tau_pub) and the CTAs that
+  // stream the SAME gallery part sit on neighbouring SMs and run in step, so the part is fetched
+  // from HBM once and served to the others from L2.
+  const int per_group = n_parts * m_group;
+  const int rem = static_cast<int>(blockIdx.x) % per_group;
+  const int m_tile = (static_cast<int>(blockIdx.x) / per_group) * m_group + rem % m_group;
+  const int part = rem / m_group;
+  if (m_tile >= m_tiles) return;  // padding CTAs of the last group (whole CTA exits before any barrier)
   const int tile_begin = part * tiles_per_part;
   const int tile_end = min(tile_begin + tiles_per_part, tiles_total);
   const int num_tiles = tile_end - tile_begin;
@@ -655,6 +661,12 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
   plan->m_tiles = m_tiles;
   plan->n_parts = n_parts;
   plan->n_lists = n_parts * kEpiGroups;
+  {  // query tiles per wave: as many as fit next to all parts, at least 1
+    int g = num_sms / n_parts;
+    if (g < 1) g = 1;
+    if (g > m_tiles) g = m_tiles;
+    plan->m_group = g;
+  }
   plan->tiles_per_part = tiles_per_part;
   plan->cap = cap;
   plan->cand_bytes = static_cast<size_t>(b) * plan->n_lists * cap * sizeof(uint2);
@@ -672,7 +684,7 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   const SmemPlan sp = plan_smem(d_pad);
   if (sp.num_stages < 2) return fail(MMR_EUNSUP, "gemm: embedding dimension too large for the shared-memory plan");
   const int tiles_total = static_cast<int>((n + kBlockN - 1) / kBlockN);
-  const int grid = plan.m_tiles * plan.n_parts;
+  const int grid = ((plan.m_tiles + plan.m_group - 1) / plan.m_group) * plan.m_group * plan.n_parts;
   auto kern = sp.resident ? gemm_topk_kernel<true> : gemm_topk_kernel<false>;
   MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sp.total)));
   // threshold exchange: rank published per part and refresh period (in gallery tiles)
@@ -680,12 +692,13 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   // measure the TMA + MMA pipeline alone
   static const int debug_flags = std::getenv("MMR_B200_GEMM_DEBUG") ? std::atoi(std::getenv("MMR_B200_GEMM_DEBUG")) : 0;
   const int pub_rank = (k + plan.n_lists - 1) / plan.n_lists;
-  const int refresh = plan.n_lists <= 48 ? 1 : (plan.n_lists + 47) / 48;
+  // every 4th tile of a warpgroup is enough (the bound only tightens; a stale value just prunes less)
+  const int refresh = plan.n_lists <= 64 ? 4 : 4 * ((plan.n_lists + 63) / 64);
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
   MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));
   kern<<<grid, kNumThreads, sp.total, stream>>>(tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap,
-                                                plan.m_tiles, plan.n_parts, plan.tiles_per_part, tiles_total,
+                                                plan.m_tiles, plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total,
                                                 sp.num_stages, pub_rank, refresh, debug_flags,
                                                 reinterpret_cast<uint2*>(cand), counts, tau_pub);
   MMR_LAUNCHED();

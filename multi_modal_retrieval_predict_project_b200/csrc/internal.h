@@ -72,6 +72,7 @@ int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, in
 // gemm_topk.cu: tcgen05 GEMM + fused top-K (bf16 storage).
 struct GemmPlan {
   int m_tiles;          // query tiles of 128
+  int m_group;          // query tiles scheduled together (one wave covers m_group x n_parts CTAs)
   int n_parts;          // gallery parts (CTAs per query tile)
   int n_lists;          // candidate lists per query (parts x epilogue warpgroups)
   int tiles_per_part;   // gallery tiles of 256 rows per part
