@@ -47,10 +47,11 @@ class ShardedSearcher:
     to the shard's first global row).  Works with any initialised ``torch.distributed`` process
     group whose backend supports CUDA tensors (NCCL); with world size 1 it is a pass-through."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, merge=None):
         import torch.distributed as dist
         self.engine = engine
         self.group = group
+        self._merge = merge if merge is not None else merge_topk  # injectable for the CPU/gloo plumbing tests
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self._gs = self._gr = None
 
@@ -62,11 +63,12 @@ class ShardedSearcher:
             return rows, scores
         b = rows.shape[0]
         if self._gs is None or self._gs.shape[1:] != scores.shape:
-            self._gs = torch.empty((self.world, b, K), dtype=torch.float32, device=scores.device)
+            self._gs = torch.empty((self.world, b, K), dtype=scores.dtype, device=scores.device)
             self._gr = torch.empty((self.world, b, K), dtype=torch.int64, device=scores.device)
-        dist.all_gather_into_tensor(self._gs, scores, group=self.group)
-        dist.all_gather_into_tensor(self._gr, rows, group=self.group)
-        return merge_topk(self._gs, self._gr, K)
+        # concatenated-along-dim-0 output form (accepted by both NCCL and gloo); rank-major == list-major
+        dist.all_gather_into_tensor(self._gs.view(self.world * b, K), scores.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(self._gr.view(self.world * b, K), rows.contiguous(), group=self.group)
+        return self._merge(self._gs, self._gr, K)
 
     def rerank(self, reranker, q_embs, rows, q_rec, cand_rec, topk: int = 0):
         """Rerank merged global candidates: the label/KG tables are replicated, the candidate

@@ -1,0 +1,60 @@
+"""2-GPU (NCCL) check of the sharded path: per-rank shard search + all-gather + on-device merge
++ sharded rerank == the single-GPU result.  Skipped unless two GPUs are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, synth
+    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher, shard_bounds
+    from oracle import search as osr
+    n, d, b, k = 40001, 256, 70, 50
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=5))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=6))
+    rng = np.random.default_rng(7)
+    masks = rng.integers(0, 2 ** 43, size=n + b, dtype=np.uint64) & rng.integers(0, 2 ** 43, size=n + b, dtype=np.uint64)
+    kg = rng.standard_normal((n + b, 64)).astype(np.float32)
+    kg /= np.linalg.norm(kg, axis=1, keepdims=True) + 1e-12
+    lo, hi = shard_bounds(n, world, rank)
+    eng = B200RetrievalEngine.from_arrays(g[lo:hi], dtype="bfloat16", device=rank, row_offset=lo)
+    rer = Reranker.from_tables(masks, kg, device=rank)
+    s = ShardedSearcher(eng)
+    qd = torch.from_numpy(q).cuda()
+    rows, scores = s.search(qd, k)
+    q_rec = torch.arange(n, n + b, device="cuda")
+    order, sc = s.rerank(rer, qd, rows, q_rec, rows.clone(), topk=20)
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), rows=rows.cpu().numpy(), scores=scores.cpu().numpy(),
+             order=order.cpu().numpy(), sc=sc.cpu().numpy())
+    if rank == 0:  # single-shard reference on the same device
+        full = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
+        r1, s1 = full.search(qd, k)
+        o1, c1 = rer.rerank_device(full, qd, r1, q_rec, r1.clone(), topk=20)
+        np.savez(os.path.join(out_dir, "single.npz"), rows=r1.cpu().numpy(), scores=s1.cpu().numpy(),
+                 order=o1.cpu().numpy(), sc=c1.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_equals_single(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    single = np.load(tmp_path / "single.npz")
+    for rank in range(2):
+        z = np.load(tmp_path / f"r{rank}.npz")
+        assert np.array_equal(z["rows"], single["rows"]) and np.array_equal(z["scores"], single["scores"])
+        assert np.array_equal(z["order"], single["order"]) and np.allclose(z["sc"], single["sc"], rtol=0, atol=1e-12)
