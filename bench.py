@@ -320,13 +320,25 @@ def main():
         pass
     n_local = hi - lo
     kern_avg_ms = kern_ms / max(kern_n, 1)
+    traffic_tbl = {}
+    try:
+        traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+
+    def traffic_for(kernel, batch, kk):
+        t = traffic_tbl.get(kernel)
+        if t and (t["rows"], t["dim"], t["batch"], t["k"], t["n_gpus"]) == (args.rows, args.dim, batch, kk, world):
+            return t["bytes"]
+        return None
+
     flops = 2.0 * b * n_local * args.dim
     use_gemm = (args.algo == "gemm") or (args.algo == "auto" and b >= 16 and n_local >= 4096)
     if use_gemm:
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (kern_avg_ms / 1e3) / 1e12 if kern_avg_ms > 0 else 0.0
         roofline = {"kernel": "gemm_topk_kernel (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic_for("gemm_topk_kernel", b, k),
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback", "peak_burst": peaks.get("bf16_tflops"),
                     "kernel_ms": kern_avg_ms, "kernel_share_of_step": kern_ms / elapsed_ms if elapsed_ms else None,
@@ -369,6 +381,7 @@ def main():
                                     "roofline": {"bound": "hbm", "achieved": byts / (scan_ms / 1e3) / 1e9,
                                                  "peak": hbm, "unit": "GB/s",
                                                  "frac": byts / (scan_ms / 1e3) / 1e9 / hbm,
+                                                 "traffic": traffic_for("scan_topk_kernel", 1, 10),
                                                  "algorithmic_bytes_per_launch": byts}}
         if rank == 0 and not args.no_cpu_baseline:
             del gallery
