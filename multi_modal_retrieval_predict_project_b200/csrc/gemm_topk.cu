@@ -52,6 +52,7 @@ constexpr int kEpiThreads = 128;                  // threads per epilogue warpgr
 constexpr int kFirstEpiWarp = 4;
 constexpr int kNumThreads = 128 + kEpiGroups * kEpiThreads;  // 384
 constexpr int kRegsLow = 40, kRegsHigh = 232;     // 128*40 + 256*232 = 64512 <= 65536
+constexpr int kTrack = 8;                         // per-thread running top-8 used to publish pruning bounds
 
 struct __align__(16) SmemAux {
   float ginv[kAccStages][kBlockN];  // first: read as float4
@@ -474,6 +475,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint2* ptr = buf;                                // append cursor (count = ptr - buf)
     float tau_local = q_ok ? -INFINITY : INFINITY;   // pre-threshold from this list's own k-th best (strict)
     float tau_pre = tau_local;                       // effective conservative threshold on acc * inv_norm(g)
+    // running top-8 of the best-of-chunk final scores this thread has appended (a subset of its list,
+    // so its r-th entry is a valid, always-current lower bound on the list's r-th best): lets the list
+    // publish its pruning bound without waiting for the next compaction
+    float top[kTrack];
+#pragma unroll
+    for (int i = 0; i < kTrack; ++i) top[i] = -INFINITY;
+    float published = -INFINITY;
+    const bool track = tau_pub != nullptr && pub_rank <= kTrack && q_ok;
     const int epi_tid = threadIdx.x - (kFirstEpiWarp * 32 + group * kEpiThreads);  // 0..127
     const int64_t range_end = min(static_cast<int64_t>(tile_end) * kBlockN, n);
     const uint32_t full_bytes = static_cast<uint32_t>(cap - 32) * 8u;
@@ -540,6 +549,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const uint32_t colbase = static_cast<uint32_t>(n0) + static_cast<uint32_t>(c * 32);
 #pragma unroll
           for (int j = 0; j < 32; ++j) score_step(ptr, tv[j], tau_pre, qinv, colbase + j);
+          if (track && m > tau_pre) {  // m was appended above: fold it into the running top-8 and publish
+            float x = m * qinv;
+#pragma unroll
+            for (int i = 0; i < kTrack; ++i) {
+              const float hi = fmaxf(top[i], x);
+              x = fminf(top[i], x);
+              top[i] = hi;
+            }
+            float rth = top[0];
+#pragma unroll
+            for (int i = 1; i < kTrack; ++i) rth = (i == pub_rank - 1) ? top[i] : rth;
+            if (rth > published) {
+              published = rth;
+              __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
+            }
+          }
           // make room for the next 32 columns: compact every list of this warp that is nearly full
           const uint32_t used =
               static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ptr) - reinterpret_cast<uintptr_t>(buf));
@@ -557,7 +582,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               ptr = buf + k;
               tau_local = pre_threshold(new_tau, qinv);
               tau_pre = fmaxf(tau_pre, tau_local);
-              if (tau_pub != nullptr) __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
+              if (tau_pub != nullptr && rth > published) {
+                published = rth;
+                __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
+              }
             }
           }
         }
@@ -693,7 +721,7 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   static const int debug_flags = std::getenv("MMR_B200_GEMM_DEBUG") ? std::atoi(std::getenv("MMR_B200_GEMM_DEBUG")) : 0;
   const int pub_rank = (k + plan.n_lists - 1) / plan.n_lists;
   // every 4th tile of a warpgroup is enough (the bound only tightens; a stale value just prunes less)
-  const int refresh = plan.n_lists <= 64 ? 4 : 4 * ((plan.n_lists + 63) / 64);
+  const int refresh = plan.n_lists <= 64 ? 2 : 2 * ((plan.n_lists + 63) / 64);
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
   MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));
