@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--kg-dim", type=int, default=300)
     ap.add_argument("--algo", default="auto")
@@ -291,18 +291,21 @@ def main():
     value = b * args.steps / (elapsed_ms / 1e3)
 
     # ---------------- end to end: pinned host queries in, host results out, every step ---------
-    out_host = None
+    out_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in out]   # pinned result buffers
+    qd = torch.empty_like(q_dev)
+
+    def e2e_step():
+        qd.copy_(q_host, non_blocking=True)              # H2D of this step's queries (pinned source)
+        res = step(qd)
+        for h, r in zip(out_host, res):
+            h.copy_(r, non_blocking=True)                # D2H of this step's results
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()                                           # untimed warm-up of the copy path
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
     for _ in range(args.steps):
-        qd = q_host.to(dev, non_blocking=True)
-        res = step(qd)
-        if out_host is None:
-            out_host = [torch.empty(r.shape, dtype=r.dtype).pin_memory() for r in res]
-        for h, r in zip(out_host, res):
-            h.copy_(r, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     d2h = sum(h.numel() * h.element_size() for h in out_host)
