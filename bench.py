@@ -194,6 +194,15 @@ def cpu_reference_run(args, steps, warmup):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's
+    # version banner) is routed to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,7 +223,7 @@ def main():
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import numpy as np
@@ -253,10 +262,9 @@ def main():
     torch.cuda.synchronize()
 
     def step(q):
-        rows, scores = searcher.search(q, k)
         if reranker is None:
-            return rows, scores
-        order, sc = searcher.rerank(reranker, q, rows, q_rec, rows, topk=k)  # record index == global row
+            return searcher.search(q, k)
+        rows, _scores, order, sc = searcher.search_rerank(reranker, q, k, q_rec, topk=k)  # record index == global row
         return rows, order, sc
 
     def barrier():
@@ -390,7 +398,7 @@ def main():
             del gallery
             line["cpu_baseline"] = cpu_reference_run(args, 3, 1)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

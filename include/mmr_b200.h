@@ -115,6 +115,14 @@ int mmr_merge_topk(const float* scores, const int64_t* rows, int32_t n_lists, in
                    int32_t k_out, float* out_scores, int64_t* out_rows, int32_t* out_src,
                    int32_t device, void* stream);
 
+/* Same merge for lists that are not packed back to back: list l starts l * stride ELEMENTS after
+ * the base pointer (device pointers).  Lets each rank all-gather ONE blob holding its scores, rows
+ * and rerank payload, and merge straight out of the gathered buffer. */
+int mmr_merge_topk_strided(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in,
+                           int64_t scores_list_stride, int64_t rows_list_stride, int32_t k_out,
+                           float* out_scores, int64_t* out_rows, int32_t* out_src, int32_t device,
+                           void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Rerank.  Replaces Reranker.rerank (Retrieval/reranker.py:240-333).
  * Tables (built once, Reranker.__init__/_load_kg :29-129): per record `label_words` uint64
@@ -140,6 +148,17 @@ int mmr_rerank_features(const mmr_index* index, const mmr_rerank_tables* tables,
                         const float* cand_emb, const int64_t* cand_rows, const int64_t* q_rec,
                         const int64_t* cand_rec, const int32_t* cand_count, int32_t b, int32_t k,
                         int32_t d, double* out_raw, uint8_t* owned, void* stream);
+/* Sharded path: the fp32 cosine(q_emb, gallery row) of b x k candidates given by GLOBAL row id
+ * (safe_cos, reranker.py:135-142) for the rows this shard owns (0 and owned = 0 elsewhere); each
+ * rank evaluates it for its LOCAL top-K before the exchange so it can travel with the lists. */
+int mmr_candidate_cosine(const mmr_index* index, const float* q_emb, const int64_t* cand_rows, int32_t b,
+                         int32_t k, int32_t d, float* out_cos, uint8_t* owned, void* stream);
+/* mmr_rerank with the embedding cosines supplied (b, k) fp32 instead of recomputed: label Jaccard
+ * and KG cosine come from the (replicated) tables, then the same combine. */
+int mmr_rerank_with_cos(const mmr_rerank_tables* tables, const float* emb_cos, const int64_t* q_rec,
+                        const int64_t* cand_rec, const int32_t* cand_count, int32_t b, int32_t k,
+                        double alpha, double beta, double gamma, int32_t topk, int32_t* out_order,
+                        double* out_scores, int32_t device, void* stream);
 /* min-max scale each feature over the query's candidates in fp64 (minmax_scale_list :152-159,
  * all-zeros when max == min), final = alpha*emb_n + beta*lab_n + gamma*kg_n (:325), order by final
  * descending then candidate position ascending (:327), keep topk (0 = all).  out_order (b, topk)

@@ -322,6 +322,34 @@ class Reranker:
                                                      _lib.current_stream(self.device)))
         return raw
 
+    def candidate_cosine_device(self, engine, q_embs, cand_rows, out=None):
+        """fp32 cosine(q, gallery row) of (B, K) candidates given by GLOBAL row id, for the rows
+        ``engine``'s shard owns (0 elsewhere) -- evaluated on the LOCAL top-K before the exchange."""
+        import torch
+        b, k = cand_rows.shape
+        if out is None:
+            out = torch.empty((b, k), dtype=torch.float32, device=cand_rows.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.mmr_candidate_cosine(engine._handle, _lib.ptr(q_embs), _lib.ptr(cand_rows), b, k,
+                                                      int(q_embs.shape[1]), _lib.ptr(out), None,
+                                                      _lib.current_stream(self.device)))
+        return out
+
+    def rerank_with_cos_device(self, emb_cos, q_rec, cand_rec, topk: int = 0):
+        """Rerank with the embedding cosines supplied (sharded path): label Jaccard + KG cosine from
+        the replicated tables, then the same min-max / combine / ordering."""
+        import torch
+        b, k = emb_cos.shape
+        keep = topk if 0 < topk < k else k
+        order = torch.empty((b, keep), dtype=torch.int32, device=emb_cos.device)
+        sc = torch.empty((b, keep, 4), dtype=torch.float64, device=emb_cos.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.mmr_rerank_with_cos(self._tables, _lib.ptr(emb_cos), _lib.ptr(q_rec),
+                                                     _lib.ptr(cand_rec), None, b, k, self.alpha, self.beta,
+                                                     self.gamma, int(topk), _lib.ptr(order), _lib.ptr(sc),
+                                                     self.device, _lib.current_stream(self.device)))
+        return order, sc
+
     def combine_device(self, raw, topk: int = 0):
         import torch
         b, k, _ = raw.shape

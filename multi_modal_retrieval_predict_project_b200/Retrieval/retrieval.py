@@ -213,7 +213,7 @@ class B200RetrievalEngine(RetrievalEngine):
         return ms.value, cnt.value
 
     # -- batched search (the hot path) ----------------------------------------------------------
-    def search(self, queries, K: int, exclude_rows=None, algo: Optional[str] = None):
+    def search(self, queries, K: int, exclude_rows=None, algo: Optional[str] = None, out_rows=None, out_scores=None):
         """Exact top-K for a batch.  ``queries``: numpy ``(B, D)`` / ``(D,)`` (host) or a torch
         tensor (CUDA tensors stay on the device: no host round trip).  Returns ``(rows, scores)``
         of shape ``(B, K)`` -- numpy for numpy input, CUDA tensors for CUDA input; rows are
@@ -261,7 +261,11 @@ class B200RetrievalEngine(RetrievalEngine):
                 ex = np.ascontiguousarray(exclude_rows, dtype=np.int64)
             if int(ex.shape[0]) != b:
                 raise ValueError("exclude_rows must have one entry per query")
-        if on_device:
+        if out_rows is not None:  # caller-provided (device) result buffers, e.g. views into an exchange blob
+            rows, scores = out_rows, out_scores
+            assert rows.is_contiguous() and scores.is_contiguous() and tuple(rows.shape) == (b, K) == tuple(scores.shape)
+            assert rows.dtype == torch.int64 and scores.dtype == torch.float32
+        elif on_device:
             rows = torch.empty((b, K), dtype=torch.int64, device=q.device)
             scores = torch.empty((b, K), dtype=torch.float32, device=q.device)
         else:

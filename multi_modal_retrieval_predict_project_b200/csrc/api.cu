@@ -505,8 +505,9 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
   return MMR_OK;
 }
 
-int mmr_merge_topk(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in, int32_t k_out,
-                   float* out_scores, int64_t* out_rows, int32_t* out_src, int32_t device, void* stream_v) {
+int mmr_merge_topk_strided(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in,
+                           int64_t scores_list_stride, int64_t rows_list_stride, int32_t k_out, float* out_scores,
+                           int64_t* out_rows, int32_t* out_src, int32_t device, void* stream_v) {
   MMR_REQUIRE(n_lists >= 1 && b >= 0 && k_in >= 1 && k_out >= 1, "mmr_merge_topk: bad sizes");
   if (b == 0) return MMR_OK;
   MMR_REQUIRE(scores && rows && out_scores && out_rows, "mmr_merge_topk: NULL argument");
@@ -515,19 +516,31 @@ int mmr_merge_topk(const float* scores, const int64_t* rows, int32_t n_lists, in
   DeviceGuard guard(device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   CallScope cs(stream);
-  const size_t n_in = static_cast<size_t>(n_lists) * b * k_in, n_out = static_cast<size_t>(b) * k_out;
+  const size_t per_list = static_cast<size_t>(b) * k_in, n_out = static_cast<size_t>(b) * k_out;
+  const bool contiguous = static_cast<size_t>(scores_list_stride) == per_list &&
+                          static_cast<size_t>(rows_list_stride) == per_list;
+  if (!contiguous && !(is_device_ptr(scores) && is_device_ptr(rows)))
+    return fail(MMR_EINVAL, "mmr_merge_topk_strided: strided lists must be device pointers");
   const float* d_s;
   const int64_t* d_r;
   float* d_os;
   int64_t* d_or;
   int32_t* d_src;
-  MMR_TRY(cs.in(scores, n_in, &d_s));
-  MMR_TRY(cs.in(rows, n_in, &d_r));
+  MMR_TRY(cs.in(scores, per_list * n_lists, &d_s));
+  MMR_TRY(cs.in(rows, per_list * n_lists, &d_r));
   MMR_TRY(cs.out(out_scores, n_out, &d_os));
   MMR_TRY(cs.out(out_rows, n_out, &d_or));
   MMR_TRY(cs.out(out_src, n_out, &d_src));
-  MMR_TRY(launch_merge_lists(d_s, d_r, n_lists, b, k_in, k_out, d_os, d_or, d_src, stream));
+  MMR_TRY(launch_merge_lists(d_s, d_r, n_lists, b, k_in, scores_list_stride, rows_list_stride, k_out, d_os, d_or,
+                             d_src, stream));
   return cs.finish();
+}
+
+int mmr_merge_topk(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in, int32_t k_out,
+                   float* out_scores, int64_t* out_rows, int32_t* out_src, int32_t device, void* stream_v) {
+  const int64_t per_list = static_cast<int64_t>(b) * k_in;
+  return mmr_merge_topk_strided(scores, rows, n_lists, b, k_in, per_list, per_list, k_out, out_scores, out_rows,
+                                out_src, device, stream_v);
 }
 
 int mmr_rerank_tables_create(mmr_rerank_tables** out, const uint64_t* label_masks, int32_t label_words,
@@ -587,11 +600,14 @@ int mmr_rerank_tables_destroy(mmr_rerank_tables* t) {
 static int rerank_features_impl(CallScope& cs, const mmr_index* ix, const mmr_rerank_tables* t, const float* q_emb,
                                 const float* cand_emb, const int64_t* cand_rows, const int64_t* q_rec,
                                 const int64_t* cand_rec, const int32_t* cand_count, int32_t b, int32_t k, int32_t d,
-                                double* d_raw, uint8_t* d_owned) {
-  MMR_REQUIRE(q_emb != nullptr, "Query embedding not found. Provide query_emb.");
-  if (cand_emb == nullptr && (ix == nullptr || cand_rows == nullptr))
-    return fail(MMR_EINVAL, "Please provide candidate_embs or candidate_emb_lookup.");
-  if (cand_emb == nullptr) MMR_REQUIRE(ix->d == d, "candidate_embs rows must match the index dimension");
+                                double* d_raw, uint8_t* d_owned, const float* emb_cos = nullptr,
+                                float* d_cos_out = nullptr) {
+  if (emb_cos == nullptr) {
+    MMR_REQUIRE(q_emb != nullptr, "Query embedding not found. Provide query_emb.");
+    if (cand_emb == nullptr && (ix == nullptr || cand_rows == nullptr))
+      return fail(MMR_EINVAL, "Please provide candidate_embs or candidate_emb_lookup.");
+    if (cand_emb == nullptr) MMR_REQUIRE(ix->d == d, "candidate_embs rows must match the index dimension");
+  }
   const size_t bk = static_cast<size_t>(b) * k;
   const float *d_q, *d_ce;
   const int64_t *d_cr, *d_qr, *d_crec;
@@ -602,10 +618,12 @@ static int rerank_features_impl(CallScope& cs, const mmr_index* ix, const mmr_re
   MMR_TRY(cs.in(q_rec, static_cast<size_t>(b), &d_qr));
   MMR_TRY(cs.in(cand_rec, bk, &d_crec));
   MMR_TRY(cs.in(cand_count, static_cast<size_t>(b), &d_cc));
+  const float* d_ec;
+  MMR_TRY(cs.in(emb_cos, bk, &d_ec));
   return launch_rerank_features(ix ? ix->emb : nullptr, ix ? ix->dtype : MMR_F32, ix ? ix->n : 0, ix ? ix->d_pad : 0,
                                 ix ? ix->row_offset : 0, t ? t->masks : nullptr, t ? t->label_words : 0,
                                 t ? t->kg : nullptr, t ? t->d_kg : 0, t ? t->n_rec : 0, d_q, d_ce, d_cr, d_qr, d_crec,
-                                d_cc, b, k, d, d_raw, d_owned, cs.stream);
+                                d_cc, b, k, d, d_raw, d_owned, d_ec, d_cos_out, cs.stream);
 }
 
 int mmr_rerank_features(const mmr_index* ix, const mmr_rerank_tables* t, const float* q_emb, const float* cand_emb,
@@ -669,6 +687,51 @@ int mmr_rerank(const mmr_index* ix, const mmr_rerank_tables* t, const float* q_e
   double* d_raw = static_cast<double*>(raw_v);
   MMR_TRY(rerank_features_impl(cs, ix, t, q_emb, cand_emb, cand_rows, q_rec, cand_rec, cand_count, b, k, d, d_raw,
                                nullptr));
+  const int32_t* d_cc;
+  MMR_TRY(cs.in(cand_count, static_cast<size_t>(b), &d_cc));
+  int32_t* d_order;
+  double* d_sc;
+  MMR_TRY(cs.out(out_order, static_cast<size_t>(b) * keep, &d_order));
+  MMR_TRY(cs.out(out_scores, static_cast<size_t>(b) * keep * 4, &d_sc));
+  MMR_TRY(launch_rerank_combine(d_raw, d_cc, b, k, alpha, beta, gamma, topk, d_order, d_sc, cs.stream));
+  return cs.finish();
+}
+
+int mmr_candidate_cosine(const mmr_index* ix, const float* q_emb, const int64_t* cand_rows, int32_t b, int32_t k,
+                         int32_t d, float* out_cos, uint8_t* owned, void* stream_v) {
+  MMR_REQUIRE(ix != nullptr, "mmr_candidate_cosine: index is NULL");
+  MMR_REQUIRE(b >= 0 && k >= 0 && d >= 1, "mmr_candidate_cosine: bad sizes");
+  if (b == 0 || k == 0) return MMR_OK;
+  MMR_REQUIRE(q_emb && cand_rows && out_cos, "mmr_candidate_cosine: NULL argument");
+  DeviceGuard guard(ix->device);
+  CallScope cs(static_cast<cudaStream_t>(stream_v));
+  float* d_cos;
+  uint8_t* d_owned;
+  MMR_TRY(cs.out(out_cos, static_cast<size_t>(b) * k, &d_cos));
+  MMR_TRY(cs.out(owned, static_cast<size_t>(b) * k, &d_owned));
+  MMR_TRY(rerank_features_impl(cs, ix, nullptr, q_emb, nullptr, cand_rows, nullptr, nullptr, nullptr, b, k, d, nullptr,
+                               d_owned, nullptr, d_cos));
+  return cs.finish();
+}
+
+int mmr_rerank_with_cos(const mmr_rerank_tables* t, const float* emb_cos, const int64_t* q_rec,
+                        const int64_t* cand_rec, const int32_t* cand_count, int32_t b, int32_t k, double alpha,
+                        double beta, double gamma, int32_t topk, int32_t* out_order, double* out_scores,
+                        int32_t device, void* stream_v) {
+  MMR_REQUIRE(b >= 0 && k >= 0 && topk >= 0, "mmr_rerank_with_cos: bad sizes");
+  if (b == 0 || k == 0) return MMR_OK;
+  MMR_REQUIRE(emb_cos && out_order && out_scores, "mmr_rerank_with_cos: NULL argument");
+  if (k > 4096) return fail(MMR_EUNSUP, "mmr_rerank_with_cos: more than 4096 candidates per query");
+  if (t != nullptr) device = t->device;
+  MMR_TRY(check_device(device, nullptr));
+  DeviceGuard guard(device);
+  CallScope cs(static_cast<cudaStream_t>(stream_v));
+  const int keep = (topk > 0 && topk < k) ? topk : k;
+  void* raw_v = nullptr;
+  MMR_TRY(cs.alloc(static_cast<size_t>(b) * k * 3 * sizeof(double), &raw_v));
+  double* d_raw = static_cast<double*>(raw_v);
+  MMR_TRY(rerank_features_impl(cs, nullptr, t, nullptr, nullptr, nullptr, q_rec, cand_rec, cand_count, b, k, 1, d_raw,
+                               nullptr, emb_cos, nullptr));
   const int32_t* d_cc;
   MMR_TRY(cs.in(cand_count, static_cast<size_t>(b), &d_cc));
   int32_t* d_order;

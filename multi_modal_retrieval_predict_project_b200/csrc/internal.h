@@ -66,8 +66,9 @@ int launch_scan(const void* emb, int dtype_store, const float* inv_norm, int64_t
 int launch_select_keys(const uint64_t* keys, int b, int64_t keys_per_query, int k_out, int64_t row_offset,
                        float* out_scores, int64_t* out_rows, cudaStream_t stream);
 // select.cu: merge (n_lists, b, k_in) (score,row) lists -> (b, k_out); out_src optional.
-int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in, int k_out,
-                       float* out_scores, int64_t* out_rows, int32_t* out_src, cudaStream_t stream);
+int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in,
+                       int64_t scores_list_stride, int64_t rows_list_stride, int k_out, float* out_scores,
+                       int64_t* out_rows, int32_t* out_src, cudaStream_t stream);
 
 // gemm_topk.cu: tcgen05 GEMM + fused top-K (bf16 storage).
 struct GemmPlan {
@@ -95,7 +96,7 @@ int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pa
                            int64_t n_rec, const float* q_emb, const float* cand_emb,
                            const int64_t* cand_rows, const int64_t* q_rec, const int64_t* cand_rec,
                            const int32_t* cand_count, int b, int k, int d, double* out_raw, uint8_t* owned,
-                           cudaStream_t stream);
+                           const float* emb_cos_in, float* cos_out, cudaStream_t stream);
 int launch_rerank_combine(const double* raw, const int32_t* cand_count, int b, int k, double alpha,
                           double beta, double gamma, int topk, int32_t* out_order, double* out_scores,
                           cudaStream_t stream);

@@ -41,7 +41,8 @@ rerank_features_kernel(const T* __restrict__ emb, int64_t n, int d_pad, int64_t 
                        int d_kg, int64_t n_rec, const float* __restrict__ q_emb, const float* __restrict__ cand_emb,
                        const int64_t* __restrict__ cand_rows, const int64_t* __restrict__ q_rec,
                        const int64_t* __restrict__ cand_rec, const int32_t* __restrict__ cand_count, int k, int d,
-                       double* __restrict__ out_raw, uint8_t* __restrict__ owned) {
+                       double* __restrict__ out_raw, uint8_t* __restrict__ owned,
+                       const float* __restrict__ emb_cos_in, float* __restrict__ cos_out) {
   const int qi = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -54,8 +55,10 @@ rerank_features_kernel(const T* __restrict__ emb, int64_t n, int d_pad, int64_t 
   const uint64_t* qmask = (q_known && label_masks != nullptr) ? label_masks + qr * label_words : nullptr;
 
   float qss = 0.f;
-  for (int i = lane; i < d; i += 32) qss = fmaf(qv[i], qv[i], qss);
-  qss = warp_sum(qss);
+  if (emb_cos_in == nullptr) {
+    for (int i = lane; i < d; i += 32) qss = fmaf(qv[i], qv[i], qss);
+    qss = warp_sum(qss);
+  }
   float qkss = 0.f;
   if (qkg != nullptr) {
     for (int i = lane; i < d_kg; i += 32) qkss = fmaf(qkg[i], qkg[i], qkss);
@@ -63,10 +66,11 @@ rerank_features_kernel(const T* __restrict__ emb, int64_t n, int d_pad, int64_t 
   }
 
   for (int j = warp; j < k; j += nwarps) {
-    double* o = out_raw + (static_cast<int64_t>(qi) * k + j) * 3;
+    double* o = out_raw != nullptr ? out_raw + (static_cast<int64_t>(qi) * k + j) * 3 : nullptr;
     if (j >= count) {
       if (lane == 0) {
-        o[0] = 0.0; o[1] = 0.0; o[2] = 0.0;
+        if (o != nullptr) { o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; }
+        if (cos_out != nullptr) cos_out[static_cast<int64_t>(qi) * k + j] = 0.f;
         if (owned != nullptr) owned[static_cast<int64_t>(qi) * k + j] = 0;
       }
       continue;
@@ -74,7 +78,9 @@ rerank_features_kernel(const T* __restrict__ emb, int64_t n, int d_pad, int64_t 
     // --- embedding cosine
     float dot = 0.f, css = 0.f;
     bool have = true;
-    if (cand_emb != nullptr) {
+    if (emb_cos_in != nullptr) {
+      // precomputed by the rank that owns the candidate row (sharded path)
+    } else if (cand_emb != nullptr) {
       const float* c = cand_emb + (static_cast<int64_t>(qi) * k + j) * d;
       for (int i = lane; i < d; i += 32) {
         const float x = c[i];
@@ -95,7 +101,15 @@ rerank_features_kernel(const T* __restrict__ emb, int64_t n, int d_pad, int64_t 
     }
     dot = warp_sum(dot);
     css = warp_sum(css);
-    const float e = have ? safe_cos_finish(dot, qss, css) : 0.f;
+    const float e = emb_cos_in != nullptr ? emb_cos_in[static_cast<int64_t>(qi) * k + j]
+                                          : (have ? safe_cos_finish(dot, qss, css) : 0.f);
+    if (cos_out != nullptr) {  // cosine-only mode
+      if (lane == 0) {
+        cos_out[static_cast<int64_t>(qi) * k + j] = e;
+        if (owned != nullptr) owned[static_cast<int64_t>(qi) * k + j] = have ? 1 : 0;
+      }
+      continue;
+    }
     // --- label Jaccard + KG cosine
     const int64_t cr = cand_rec != nullptr ? cand_rec[static_cast<int64_t>(qi) * k + j] : -1;
     const bool c_known = cr >= 0 && cr < n_rec;
@@ -207,18 +221,19 @@ int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pa
                            const uint64_t* label_masks, int label_words, const float* kg, int d_kg, int64_t n_rec,
                            const float* q_emb, const float* cand_emb, const int64_t* cand_rows,
                            const int64_t* q_rec, const int64_t* cand_rec, const int32_t* cand_count, int b, int k,
-                           int d, double* out_raw, uint8_t* owned, cudaStream_t stream) {
+                           int d, double* out_raw, uint8_t* owned, const float* emb_cos_in, float* cos_out,
+                           cudaStream_t stream) {
   if (b == 0 || k == 0) return MMR_OK;
-  if (cand_emb == nullptr && (emb == nullptr || cand_rows == nullptr))
+  if (emb_cos_in == nullptr && cand_emb == nullptr && (emb == nullptr || cand_rows == nullptr))
     return fail(MMR_EINVAL, "Please provide candidate_embs or an index with candidate rows.");
   if (dtype_store == MMR_BF16 && cand_emb == nullptr) {
     rerank_features_kernel<__nv_bfloat16><<<b, 128, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(emb), n, d_pad, row_offset, label_masks, label_words, kg, d_kg, n_rec,
-        q_emb, cand_emb, cand_rows, q_rec, cand_rec, cand_count, k, d, out_raw, owned);
+        q_emb, cand_emb, cand_rows, q_rec, cand_rec, cand_count, k, d, out_raw, owned, emb_cos_in, cos_out);
   } else {
     rerank_features_kernel<float><<<b, 128, 0, stream>>>(
         static_cast<const float*>(emb), n, d_pad, row_offset, label_masks, label_words, kg, d_kg, n_rec, q_emb,
-        cand_emb, cand_rows, q_rec, cand_rec, cand_count, k, d, out_raw, owned);
+        cand_emb, cand_rows, q_rec, cand_rec, cand_count, k, d, out_raw, owned, emb_cos_in, cos_out);
   }
   MMR_LAUNCHED();
   return MMR_OK;

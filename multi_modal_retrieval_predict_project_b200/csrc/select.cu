@@ -41,17 +41,18 @@ struct KeySourceVar {  // GEMM candidates: (b, n_parts, cap) raw {score bits, lo
   }
 };
 
-struct KeySourceLists {  // (n_lists, b, k_in) score/row pairs with GLOBAL rows
+struct KeySourceLists {  // n_lists x (b, k_in) score/row pairs with GLOBAL rows; list l starts at l * stride
   const float* scores;
   const int64_t* rows;
   int n_lists, b, k_in;
+  int64_t s_stride, r_stride;  // elements between consecutive lists
   __device__ __forceinline__ int64_t count(int) const { return static_cast<int64_t>(n_lists) * k_in; }
   __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
     const int l = static_cast<int>(i / k_in);
     const int j = static_cast<int>(i - static_cast<int64_t>(l) * k_in);
-    const int64_t at = (static_cast<int64_t>(l) * b + q) * k_in + j;
-    const int64_t r = rows[at];
-    return r < 0 ? 0ull : make_key(scores[at], static_cast<uint32_t>(r));
+    const int64_t at = static_cast<int64_t>(q) * k_in + j;
+    const int64_t r = rows[l * r_stride + at];
+    return r < 0 ? 0ull : make_key(scores[l * s_stride + at], static_cast<uint32_t>(r));
   }
 };
 
@@ -238,9 +239,10 @@ int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_
                        nullptr, stream);
 }
 
-int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in, int k_out,
-                       float* out_scores, int64_t* out_rows, int32_t* out_src, cudaStream_t stream) {
-  KeySourceLists src{scores, rows, n_lists, b, k_in};
+int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in,
+                       int64_t scores_list_stride, int64_t rows_list_stride, int k_out, float* out_scores,
+                       int64_t* out_rows, int32_t* out_src, cudaStream_t stream) {
+  KeySourceLists src{scores, rows, n_lists, b, k_in, scores_list_stride, rows_list_stride};
   return launch_select(src, b, static_cast<int64_t>(n_lists) * k_in, k_out, 0, out_scores, out_rows, out_src,
                        stream);
 }

@@ -70,6 +70,50 @@ class ShardedSearcher:
         dist.all_gather_into_tensor(self._gr.view(self.world * b, K), rows.contiguous(), group=self.group)
         return self._merge(self._gs, self._gr, K)
 
+    def search_rerank(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
+        """The whole sharded step with ONE collective.  Every rank: local top-K, the fp32 embedding
+        cosine of its own K candidates (all rows are local), then a single NCCL all-gather of one
+        blob per rank ``[scores f32 | cosines f32 | rows i64]``; the strided on-device merge reads
+        the gathered blobs in place and reports where each winner came from, the cosines follow
+        through that index, and label/KG features come from the replicated tables.  The record index
+        of a candidate is its global row id.  Returns ``(rows, scores, order, rerank_scores)``."""
+        import torch
+        import torch.distributed as dist
+        eng = self.engine
+        b = int(queries.shape[0])
+        if self.world == 1:
+            rows, scores = eng.search(queries, K, algo=algo)
+            order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
+            return rows, scores, order, sc
+        bk = b * K
+        dev = queries.device
+        if getattr(self, "_blob", None) is None or self._blob.numel() != bk * 16:
+            self._blob = torch.empty(bk * 16, dtype=torch.uint8, device=dev)
+            self._gblob = torch.empty(self.world * bk * 16, dtype=torch.uint8, device=dev)
+        f = self._blob[: bk * 8].view(torch.float32)
+        scores_v, cos_v = f[:bk].view(b, K), f[bk:].view(b, K)
+        rows_v = self._blob[bk * 8:].view(torch.int64).view(b, K)
+        eng.search(queries, K, algo=algo, out_rows=rows_v, out_scores=scores_v)
+        reranker.candidate_cosine_device(eng, queries, rows_v, out=cos_v)
+        dist.all_gather_into_tensor(self._gblob, self._blob, group=self.group)
+        gf = self._gblob.view(torch.float32)            # per-rank stride: 4*bk floats
+        gi = self._gblob.view(torch.int64)              # per-rank stride: 2*bk int64, rows start at +bk
+        out_s = torch.empty((b, K), dtype=torch.float32, device=dev)
+        out_r = torch.empty((b, K), dtype=torch.int64, device=dev)
+        src = torch.empty((b, K), dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        d = dev.index or 0
+        with torch.cuda.device(d):
+            _lib.check(lib.mmr_merge_topk_strided(gf.data_ptr(), gi.data_ptr() + bk * 8, self.world, b, K, 4 * bk,
+                                                  2 * bk, K, _lib.ptr(out_s), _lib.ptr(out_r), _lib.ptr(src), d,
+                                                  _lib.current_stream(d)))
+        srcl = src.long().clamp_(min=0)
+        qoff = torch.arange(b, device=dev, dtype=torch.int64).unsqueeze(1) * K
+        cos_idx = (srcl // K) * (4 * bk) + bk + qoff + (srcl % K)
+        cos = gf[cos_idx.reshape(-1)].view(b, K).contiguous()
+        order, sc = reranker.rerank_with_cos_device(cos, q_rec, out_r, topk)
+        return out_r, out_s, order, sc
+
     def rerank(self, reranker, q_embs, rows, q_rec, cand_rec, topk: int = 0):
         """Rerank merged global candidates: the label/KG tables are replicated, the candidate
         embedding cosine is computed by the rank that owns the row and summed across ranks
