@@ -126,19 +126,49 @@ __device__ __forceinline__ uint64_t warp_topk_threshold(const uint64_t (&key)[E]
   return prefix;  // 0 when fewer than k valid keys: everything non-zero survives
 }
 
-template <int E>
-__device__ __forceinline__ void warp_write_survivors(const uint64_t (&key)[E], uint64_t thr, uint64_t* dst, int cap,
-                                                     int lane) {
+// survivors (key >= thr) of a warp's register-resident keys -> dst[0..cap), with the index each key
+// came from (idx_of(e) for register slot e of this lane) carried along; the tail is zero padded
+template <int E, typename IdxFn>
+__device__ __forceinline__ void warp_write_survivors(const uint64_t (&key)[E], uint64_t thr, uint64_t* dst,
+                                                     int32_t* dst_idx, int cap, int lane, IdxFn idx_of) {
   int base = 0;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     const bool keep = key[e] >= thr && key[e] != 0ull;
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
     const int pos = base + __popc(m & ((1u << lane) - 1u));
-    if (keep && pos < cap) dst[pos] = key[e];
+    if (keep && pos < cap) {
+      dst[pos] = key[e];
+      dst_idx[pos] = idx_of(e);
+    }
     base += __popc(m);
   }
-  for (int i = base + lane; i < cap; i += 32) dst[i] = 0ull;
+  for (int i = base + lane; i < cap; i += 32) {
+    dst[i] = 0ull;
+    dst_idx[i] = -1;
+  }
+}
+
+// warp bitonic sort (descending) of n keys with a 32-bit payload
+__device__ __forceinline__ void warp_bitonic_sort_desc_kv(uint64_t* s, int32_t* v, int n, int lane) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n; i += kWarp) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = s[i], b = s[ixj];
+          if ((a < b) == ((i & k) == 0)) {
+            s[i] = b;
+            s[ixj] = a;
+            const int32_t t = v[i];
+            v[i] = v[ixj];
+            v[ixj] = t;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 template <typename Source>
@@ -146,7 +176,9 @@ __global__ void __launch_bounds__(256)
 select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict__ out_scores,
                    int64_t* __restrict__ out_rows, int32_t* __restrict__ out_src) {
   __shared__ __align__(16) uint64_t lvl2[8 * 128];
+  __shared__ int32_t lvl2_idx[8 * 128];
   __shared__ __align__(16) uint64_t fin[128];
+  __shared__ int32_t fin_idx[128];
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = src.count(q);
@@ -158,7 +190,8 @@ select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict_
       key[e] = i < total ? src.get(q, i) : 0ull;
     }
     const uint64_t thr = warp_topk_threshold<16>(key, k_out);
-    warp_write_survivors<16>(key, thr, lvl2 + warp * 128, 128, lane);
+    warp_write_survivors<16>(key, thr, lvl2 + warp * 128, lvl2_idx + warp * 128, 128, lane,
+                             [&](int e) { return warp * 512 + e * 32 + lane; });
   }
   __syncthreads();
   if (warp == 0) {
@@ -166,9 +199,9 @@ select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict_
 #pragma unroll
     for (int e = 0; e < 32; ++e) key[e] = lvl2[e * 32 + lane];
     const uint64_t thr = warp_topk_threshold<32>(key, k_out);
-    warp_write_survivors<32>(key, thr, fin, 128, lane);
+    warp_write_survivors<32>(key, thr, fin, fin_idx, 128, lane, [&](int e) { return lvl2_idx[e * 32 + lane]; });
     __syncwarp();
-    warp_bitonic_sort_desc(fin, 128, lane);
+    warp_bitonic_sort_desc_kv(fin, fin_idx, 128, lane);
     for (int i = lane; i < k_out; i += 32) {
       const uint64_t k64 = fin[i];
       const int64_t o = static_cast<int64_t>(q) * k_out + i;
@@ -179,16 +212,7 @@ select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict_
       } else {
         out_scores[o] = key_score(k64);
         out_rows[o] = row_offset + static_cast<int64_t>(key_row(k64));
-        if (out_src != nullptr) {
-          int found = -1;
-          for (int64_t j = 0; j < total; ++j) {
-            if (src.get(q, j) == k64) {
-              found = static_cast<int>(j);
-              break;
-            }
-          }
-          out_src[o] = found;
-        }
+        if (out_src != nullptr) out_src[o] = fin_idx[i];
       }
     }
   }
