@@ -532,6 +532,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // fast path: t_j = acc_j * inv_norm(g_j) and the chunk maximum (NaN = out-of-range column,
         // ignored by fmaxf); almost every chunk ends here once the threshold has tightened
         float tv[32];
+        float gm[8];  // maxima of the 8 groups of 4 columns
         float m = -INFINITY;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -543,12 +544,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           tv[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) * g1;
           tv[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) * g2;
           tv[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) * g3;
-          m = fmaxf(m, fmaxf(fmaxf(tv[j4 * 4 + 0], tv[j4 * 4 + 1]), fmaxf(tv[j4 * 4 + 2], tv[j4 * 4 + 3])));
+          gm[j4] = fmaxf(fmaxf(tv[j4 * 4 + 0], tv[j4 * 4 + 1]), fmaxf(tv[j4 * 4 + 2], tv[j4 * 4 + 3]));
+          m = fmaxf(m, gm[j4]);
         }
         if (__any_sync(0xffffffffu, m > tau_pre)) {  // warp-uniform
           const uint32_t colbase = static_cast<uint32_t>(n0) + static_cast<uint32_t>(c * 32);
+          // second-level filter: only the groups of 4 columns in which some lane has a hit run the
+          // predicated append (typically 1-3 of 8)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) score_step(ptr, tv[j], tau_pre, qinv, colbase + j);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (__any_sync(0xffffffffu, gm[j4] > tau_pre)) {
+              score_step(ptr, tv[j4 * 4 + 0], tau_pre, qinv, colbase + j4 * 4 + 0);
+              score_step(ptr, tv[j4 * 4 + 1], tau_pre, qinv, colbase + j4 * 4 + 1);
+              score_step(ptr, tv[j4 * 4 + 2], tau_pre, qinv, colbase + j4 * 4 + 2);
+              score_step(ptr, tv[j4 * 4 + 3], tau_pre, qinv, colbase + j4 * 4 + 3);
+            }
+          }
           if (track && m > tau_pre) {  // m was appended above: fold it into the running top-8 and publish
             float x = m * qinv;
 #pragma unroll

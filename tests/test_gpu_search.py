@@ -225,3 +225,15 @@ def test_gemm_duplicates_and_zero_rows():
         assert np.all(scores[5] == 0.0) and np.array_equal(rows[5], np.arange(50)), algo
         want_rows, want_scores = osr.exact_topk(q, g, 50)
         _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+
+
+def test_gemm_large_k_generic_compaction():
+    """k > 256 uses 4096-entry candidate lists and the generic (re-reading) compaction path."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(30000, 128, seed=101))
+    q = osr.to_bf16_round(synth.make_embeddings(20, 128, seed=102))
+    eng = _engine(g, dtype="bfloat16")
+    for k in (300, 1000):
+        rows, scores = eng.search(q, k, algo="gemm")
+        want_rows, want_scores = osr.exact_topk(q, g, k)
+        _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
