@@ -154,6 +154,17 @@ int check_device(int device, int* num_sms) {
     return fail(MMR_ENODEV, "device " + std::to_string(device) + " is sm_" + std::to_string(major) +
                                 std::to_string(minor) + "; libmmr_b200 is built for sm_100a only");
   }
+  {
+    // The handle-less entry points take their temporaries from the device's stream-ordered pool.
+    // By default the pool gives memory back to the OS at every synchronisation, which turns each
+    // synchronous call (host result buffers) into a multi-millisecond cuMemCreate/map cycle: keep it.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   if (device < kMaxDev) cached_sms[device].store(sms, std::memory_order_release);
   if (num_sms != nullptr) *num_sms = sms;
   return MMR_OK;

@@ -341,7 +341,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
                  int k, int cap, int m_tiles, int m_group, int n_parts, int tiles_per_part, int tiles_total,
                  int num_stages,
-                 int pub_rank, int refresh_tiles, int debug_flags, uint2* __restrict__ cand,
+                 int pub_rank, int refresh_tiles, int early_tiles, int debug_flags, uint2* __restrict__ cand,
                  int32_t* __restrict__ counts, uint32_t* __restrict__ tau_pub) {
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; the declaration requests it and the
   // kernel traps loudly if the runtime did not honour it (no slack bytes are budgeted).
@@ -478,9 +478,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // running top-8 of the best-of-chunk final scores this thread has appended (a subset of its list,
     // so its r-th entry is a valid, always-current lower bound on the list's r-th best): lets the list
     // publish its pruning bound without waiting for the next compaction
+    // (slots [0, kTrack - r) are pinned at +inf so that the r-th best always sits in the LAST slot:
+    // a compile-time register index -- a runtime index would push the array to local memory)
     float top[kTrack];
 #pragma unroll
-    for (int i = 0; i < kTrack; ++i) top[i] = -INFINITY;
+    for (int i = 0; i < kTrack; ++i) top[i] = (i < kTrack - pub_rank) ? INFINITY : -INFINITY;
     float published = -INFINITY;
     const bool track = tau_pub != nullptr && pub_rank <= kTrack && q_ok;
     const int epi_tid = threadIdx.x - (kFirstEpiWarp * 32 + group * kEpiThreads);  // 0..127
@@ -514,7 +516,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       // refresh the cross-CTA pruning bound (0 = "not published yet" => no pruning); purely
       // advisory and monotone, so stale reads are safe
-      if (tau_pub != nullptr && ((t >> 1) % refresh_tiles) == 0 && t >= kEpiGroups && q_ok) {
+      // (on every tile for the first `early_tiles` tiles of the group: right after start-up the bound
+      // moves fastest and an early bound keeps the lists from filling with the first few hundred rows)
+      if (tau_pub != nullptr && t >= kEpiGroups && q_ok &&
+          ((t >> 1) < early_tiles || ((t >> 1) % refresh_tiles) == 0)) {
         uint32_t g = 0xFFFFFFFFu;
         for (int p = 0; p < n_lists; ++p) {
           const uint32_t v = __ldcg(tau_pub + static_cast<int64_t>(p) * b_pad + q);
@@ -568,9 +573,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               x = fminf(top[i], x);
               top[i] = hi;
             }
-            float rth = top[0];
-#pragma unroll
-            for (int i = 1; i < kTrack; ++i) rth = (i == pub_rank - 1) ? top[i] : rth;
+            const float rth = top[kTrack - 1];
             if (rth > published) {
               published = rth;
               __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
@@ -733,12 +736,17 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   const int pub_rank = (k + plan.n_lists - 1) / plan.n_lists;
   // every 4th tile of a warpgroup is enough (the bound only tightens; a stale value just prunes less)
   const int refresh = plan.n_lists <= 64 ? 2 : 2 * ((plan.n_lists + 63) / 64);
+  // Early per-tile refresh: measured +28 % at 1M x 1024 (8 CTAs share a gallery part) but -15 % at
+  // 1M x 2048/4096 (16 sharers): without the synchronous first compaction the sharers drift apart
+  // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).  MMR_B200_EARLY_TILES overrides.
+  static const int early_env = std::getenv("MMR_B200_EARLY_TILES") ? std::atoi(std::getenv("MMR_B200_EARLY_TILES")) : -1;
+  const int early_tiles = early_env >= 0 ? early_env : (plan.m_group <= 8 ? 8 : 0);
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
   MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));
   kern<<<grid, kNumThreads, sp.total, stream>>>(tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap,
                                                 plan.m_tiles, plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total,
-                                                sp.num_stages, pub_rank, refresh, debug_flags,
+                                                sp.num_stages, pub_rank, refresh, early_tiles, debug_flags,
                                                 reinterpret_cast<uint2*>(cand), counts, tau_pub);
   MMR_LAUNCHED();
   return MMR_OK;
