@@ -109,3 +109,34 @@ def evaluate_retrieval(all_retrieved, all_relevant, k: int = 5) -> Dict[str, flo
     t = per_query_metrics([list(r) for r in all_retrieved], [list(r) for r in all_relevant], k)
     return {"P": float(np.mean(t[:, _P])), "R": float(np.mean(t[:, _R])), "mAP": float(np.mean(t[:, _AP])),
             "MRR": float(np.mean(t[:, _RR])), "nDCG": float(np.mean(t[:, _NDCG]))}
+
+
+def metrics_from_rows(retrieved_rows, rel_indptr, rel_sorted, k: int, rel_list_len=None, ret_count=None):
+    """Device-native batched metrics (BASELINE cfg5: evaluation without string ids or host lists).
+
+    ``retrieved_rows`` (Q, K) int64 row ids as returned by ``engine.search`` (-1 padding allowed),
+    relevance as CSR over row ids: ``rel_indptr`` (Q+1) int64, ``rel_sorted`` per-query sorted unique
+    int64 ids, optional ``rel_list_len`` (Q) = len(relevant) as passed (AP denominator; default =
+    unique count).  numpy arrays or CUDA tensors.  Returns the (Q, 5) fp64 table
+    ``[P@k, Recall@k, AP@k, RR, nDCG@k]`` of the same type family as the input."""
+    import torch
+    on_device = hasattr(retrieved_rows, "is_cuda") and retrieved_rows.is_cuda
+    nq, k_ret = int(retrieved_rows.shape[0]), int(retrieved_rows.shape[1])
+    kk = int(k)
+    if kk < 1:
+        raise ZeroDivisionError("division by zero")
+    tbl = np.log2(np.arange(2, max(kk, k_ret) + 2))
+    if on_device:
+        dev = retrieved_rows.device.index or 0
+        out = torch.empty((nq, 5), dtype=torch.float64, device=retrieved_rows.device)
+        retrieved_rows = retrieved_rows.contiguous()
+    else:
+        dev = _lib.require_cuda(None)
+        out = np.empty((nq, 5), dtype=np.float64)
+        retrieved_rows = np.ascontiguousarray(retrieved_rows, dtype=np.int64)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mmr_metrics(_lib.ptr(retrieved_rows), _lib.ptr(ret_count), nq, k_ret, _lib.ptr(rel_indptr),
+                                   _lib.ptr(rel_sorted), _lib.ptr(rel_list_len), kk, _lib.ptr(tbl), _lib.ptr(out), dev,
+                                   _lib.current_stream(dev)))
+    return out

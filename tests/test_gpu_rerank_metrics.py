@@ -176,3 +176,34 @@ def test_compute_ranking_metrics_matches_reference():
         mrr, hit, rec = compute_ranking_metrics(z["queries"], z["gallery"], z["test_labels"], z["train_labels"],
                                                 k=int(k_s))
         assert np.isclose(mrr, w[0], rtol=1e-9) and hit == w[1] and np.isclose(rec, w[2], rtol=1e-9)
+
+
+def test_device_native_metrics_cfg5_style():
+    """cfg5 at reduced scale: search results (CUDA tensor of row ids) + CSR relevance on the device ->
+    metrics identical to the oracle."""
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, synth
+    from multi_modal_retrieval_predict_project_b200.Helpers import metrics_from_rows
+    n, d, nq, k = 20000, 128, 300, 100
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=33))
+    q = osr.to_bf16_round(synth.make_embeddings(nq, d, seed=34))
+    eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
+    rows, _ = eng.search(torch.from_numpy(q).cuda(), k)
+    rng = np.random.default_rng(35)
+    sizes = rng.integers(0, 201, size=nq)
+    indptr = np.zeros(nq + 1, np.int64); indptr[1:] = np.cumsum(sizes)
+    rel = np.concatenate([np.sort(rng.choice(n, size=s, replace=False)) for s in sizes] + [np.zeros(0, np.int64)]).astype(np.int64)
+    # make sure some relevant ids are actually retrieved
+    r_host = rows.cpu().numpy()
+    for i in range(0, nq, 3):
+        if sizes[i] >= 3:
+            seg = rel[indptr[i]:indptr[i + 1]]
+            seg[:3] = r_host[i, [0, 7, 50]]
+            rel[indptr[i]:indptr[i + 1]] = np.unique(seg).tolist() + [n + j for j in range(len(seg) - len(np.unique(seg)))]
+            rel[indptr[i]:indptr[i + 1]] = np.sort(rel[indptr[i]:indptr[i + 1]])
+    for kk in (10, 100):
+        got = metrics_from_rows(rows, torch.from_numpy(indptr).cuda(), torch.from_numpy(rel).cuda(), kk).cpu().numpy()
+        rets = [[int(x) for x in r_host[i]] for i in range(nq)]
+        rels = [rel[indptr[i]:indptr[i + 1]].tolist() for i in range(nq)]
+        assert np.array_equal(got, om.per_query_table(rets, rels, kk))
+        assert got[:, 0].sum() > 0
