@@ -467,7 +467,10 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
   }
 
   int use = algo;
-  if (use == MMR_ALGO_AUTO) use = (ix->dtype == MMR_BF16 && b >= 16 && ix->n >= 4096) ? MMR_ALGO_GEMM : MMR_ALGO_SCAN;
+  // measured on 10M x 512 (scripts/sweep_batch.py): the TMA-fed GEMM kernel stays HBM-bound and flat
+  // (1.5-1.9 ms) from b = 2 to b = 128 while the scan re-streams the gallery per query group; b = 1 is the
+  // scan's latency path
+  if (use == MMR_ALGO_AUTO) use = (ix->dtype == MMR_BF16 && b >= 2 && ix->n >= 1024) ? MMR_ALGO_GEMM : MMR_ALGO_SCAN;
 
   if (use == MMR_ALGO_GEMM) {
     GemmPlan gp;

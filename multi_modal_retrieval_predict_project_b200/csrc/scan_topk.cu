@@ -177,7 +177,10 @@ scan_topk_kernel(const T* __restrict__ emb, const float* __restrict__ inv_norm, 
 template <typename T, int CH, int QB>
 int launch_one(const T* emb, const float* inv_norm, int64_t n, int d_pad, const float* q, const float* q_inv,
                int b, int k, const int64_t* excl, const ScanPlan& plan, uint64_t* partial, cudaStream_t stream) {
-  constexpr int R = (CH >= 8) ? 1 : (8 / CH > 4 ? 4 : 8 / CH);
+  // rows in flight per warp: 8 x 1 KiB for the batch-1 bf16 d=512 case (16 warps => 128 KiB per SM in
+  // flight), fewer when the query registers (QB x CH x V) leave less room
+  constexpr int kRowRegs = (QB == 1) ? 16 : 8;  // uint4 registers spent on in-flight rows
+  constexpr int R = (kRowRegs / CH) < 1 ? 1 : (kRowRegs / CH > 8 ? 8 : kRowRegs / CH);
   auto kern = scan_topk_kernel<T, CH, QB, R>;
   MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem)));
   dim3 grid(plan.n_parts, (b + QB - 1) / QB);
