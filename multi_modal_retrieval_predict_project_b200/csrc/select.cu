@@ -171,10 +171,13 @@ __device__ __forceinline__ void warp_bitonic_sort_desc_kv(uint64_t* s, int32_t* 
   }
 }
 
+// grid = (queries, chunks): chunk c selects among candidates [c * 4096, (c + 1) * 4096).  With
+// `stage_keys` != nullptr the (<= 128, zero padded) surviving keys go to stage_keys[q][c][128] for a
+// second pass instead of being decoded into scores / rows.
 template <typename Source>
 __global__ void __launch_bounds__(256)
 select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict__ out_scores,
-                   int64_t* __restrict__ out_rows, int32_t* __restrict__ out_src) {
+                   int64_t* __restrict__ out_rows, int32_t* __restrict__ out_src, uint64_t* __restrict__ stage_keys) {
   __shared__ __align__(16) uint64_t lvl2[8 * 128];
   __shared__ int32_t lvl2_idx[8 * 128];
   __shared__ __align__(16) uint64_t fin[128];
@@ -182,11 +185,12 @@ select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict_
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = src.count(q);
+  const int64_t chunk_base = static_cast<int64_t>(blockIdx.y) * 4096;
   {
     uint64_t key[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-      const int64_t i = static_cast<int64_t>(warp) * 512 + e * 32 + lane;
+      const int64_t i = chunk_base + static_cast<int64_t>(warp) * 512 + e * 32 + lane;
       key[e] = i < total ? src.get(q, i) : 0ull;
     }
     const uint64_t thr = warp_topk_threshold<16>(key, k_out);
@@ -201,6 +205,11 @@ select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict_
     const uint64_t thr = warp_topk_threshold<32>(key, k_out);
     warp_write_survivors<32>(key, thr, fin, fin_idx, 128, lane, [&](int e) { return lvl2_idx[e * 32 + lane]; });
     __syncwarp();
+    if (stage_keys != nullptr) {  // first pass of a two-pass selection: hand the survivors on unsorted
+      uint64_t* dst = stage_keys + (static_cast<int64_t>(q) * gridDim.y + blockIdx.y) * 128;
+      for (int i = lane; i < 128; i += 32) dst[i] = fin[i];
+      return;
+    }
     warp_bitonic_sort_desc_kv(fin, fin_idx, 128, lane);
     for (int i = lane; i < k_out; i += 32) {
       const uint64_t k64 = fin[i];
@@ -223,8 +232,26 @@ int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_o
                   int64_t* out_rows, int32_t* out_src, cudaStream_t stream) {
   if (b == 0 || k_out == 0) return MMR_OK;
   if (k_out <= 128 && per_query <= 4096) {
-    select_fast_kernel<Source><<<b, 256, 0, stream>>>(src, k_out, row_offset, out_scores, out_rows, out_src);
+    select_fast_kernel<Source><<<b, 256, 0, stream>>>(src, k_out, row_offset, out_scores, out_rows, out_src, nullptr);
     MMR_LAUNCHED();
+    return MMR_OK;
+  }
+  if (k_out <= 128 && out_src == nullptr && per_query <= 32 * 4096) {
+    // two passes: chunks of 4096 candidates -> <= 128 survivors each -> one final selection
+    const int chunks = static_cast<int>((per_query + 4095) / 4096);
+    uint64_t* stage = nullptr;
+    MMR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&stage), static_cast<size_t>(b) * chunks * 128 * sizeof(uint64_t),
+                                 stream));
+    select_fast_kernel<Source><<<dim3(b, chunks), 256, 0, stream>>>(src, k_out, row_offset, nullptr, nullptr, nullptr,
+                                                                   stage);
+    count_launch();
+    KeySourceFlat flat{stage, static_cast<int64_t>(chunks) * 128};
+    select_fast_kernel<KeySourceFlat><<<b, 256, 0, stream>>>(flat, k_out, row_offset, out_scores, out_rows, nullptr,
+                                                            nullptr);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(stage, stream);
+    if (e != cudaSuccess) return fail(MMR_ECUDA, std::string("select: ") + cudaGetErrorString(e));
     return MMR_OK;
   }
   const int keep = next_pow2(k_out);
