@@ -195,6 +195,22 @@ int mmr_label_relevance(const uint64_t* q_masks, int64_t nq, const uint64_t* g_m
                         int32_t label_words, int32_t exclude_self, uint8_t* out_relevant,
                         int32_t device, void* stream);
 
+/* Full-ranking reduction of compute_ranking_metrics (Evaluate/retrieval_overlap.py:89-100): for every
+ * query the 1-based rank of the best-scoring RELEVANT gallery row of this shard (relevant = label
+ * masks overlap; 0 if none) and the number of relevant rows (:103-112) -- two sweeps over the gallery,
+ * no (Q, N) matrix, no sort.  g_masks is (n, label_words) for this shard's rows. */
+int mmr_first_relevant_rank(mmr_index* index, const void* q, int32_t b, int32_t q_dtype, const uint64_t* q_masks,
+                            const uint64_t* g_masks, int32_t label_words, int64_t* out_rank,
+                            int64_t* out_total, void* stream);
+
+/* Result-set diversity (Evaluate/retrieval_diversity_compute.py:171-194): emb (b, k, d) fp32 ->
+ * 1 - mean pairwise cosine (compute_embedding_diversity; 0 for fewer than 2 items) and label masks
+ * (b, k, label_words) -> |union of labels| / mean label count over the items that have labels
+ * (compute_label_diversity_from_labels; 0 if none).  Either half may be omitted (NULL). */
+int mmr_result_diversity(const float* emb, const uint64_t* label_masks, const int32_t* counts, int32_t b,
+                         int32_t k, int32_t d, int32_t label_words, double* out_emb_div,
+                         double* out_label_div, int32_t device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

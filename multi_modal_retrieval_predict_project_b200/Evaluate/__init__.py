@@ -52,26 +52,87 @@ def relevance_lists(query_vals, query_ids: Sequence[str], gallery_vals, gallery_
 
 
 def compute_ranking_metrics(query_embs, gallery_embs, query_labels, gallery_labels, k: int = 1, device=None):
-    """(MRR, Hit@k, mean Recall@k) of ``retrieval_overlap.py:84-115`` with the full ranking from the
-    exact GPU search (K = N) instead of a materialised (Q, N) matrix + N-long argsorts."""
+    """(MRR, Hit@k, mean Recall@k) of ``retrieval_overlap.py:84-115``.  The rank of the first relevant
+    item over the FULL ranking comes from ``mmr_first_relevant_rank`` (two sweeps over the gallery on the
+    device, any N), the top-k from the exact search; no (Q, N) matrix, no N-long argsorts."""
+    import torch
     from ..Retrieval import B200RetrievalEngine
     g = np.ascontiguousarray(gallery_embs, dtype=np.float32)
     q = np.ascontiguousarray(query_embs, dtype=np.float32)
-    n = g.shape[0]
-    if n > _lib.MAX_K:
-        raise NotImplementedError("full-ranking metrics need K = N <= 1024 in this round")
+    n, nq = g.shape[0], q.shape[0]
+    qm = label_masks(np.asarray(query_labels))
+    gm = label_masks(np.asarray(gallery_labels))
     eng = B200RetrievalEngine.from_arrays(g, device=device)
-    rows, _ = eng.search(q, n)
+    rank = np.empty(nq, dtype=np.int64)
+    total = np.empty(nq, dtype=np.int64)
+    lib = _lib.load()
+    with torch.cuda.device(eng.device):
+        _lib.check(lib.mmr_first_relevant_rank(eng._handle, _lib.ptr(q), nq, _lib.MMR_F32, _lib.ptr(qm), _lib.ptr(gm),
+                                               qm.shape[1], _lib.ptr(rank), _lib.ptr(total),
+                                               _lib.current_stream(eng.device)))
+    kk = min(int(k), n, _lib.MAX_K)
+    rows, _ = eng.search(q, kk)
     eng.close()
-    rel = relevance_matrix(np.asarray(query_labels), np.asarray(gallery_labels), False, device).astype(bool)
-    rr, recalls, hits = [], [], 0
-    for i in range(q.shape[0]):
-        ranked_rel = rel[i][rows[i]]
-        pos = np.nonzero(ranked_rel)[0]
-        rank = int(pos[0]) + 1 if pos.size else None
-        rr.append(1.0 / rank if rank else 0.0)
-        if rank and rank <= k:
-            hits += 1
-        total = int(rel[i].sum())
-        recalls.append(int(ranked_rel[:k].sum()) / total if total > 0 else 0.0)
-    return np.mean(rr), hits / q.shape[0], np.mean(recalls)
+    valid = rows >= 0                                              # relevance of the k retrieved rows
+    overlap = np.zeros(rows.shape, dtype=bool)
+    safe_rows = np.where(valid, rows, 0)
+    for w in range(qm.shape[1]):
+        overlap |= (gm[safe_rows, w] & qm[:, w][:, None]) != 0
+    rel_topk = (overlap & valid).sum(axis=1)
+    rr = np.where(rank > 0, 1.0 / np.maximum(rank, 1), 0.0)
+    hits = int(((rank > 0) & (rank <= k)).sum())
+    recalls = np.where(total > 0, rel_topk / np.maximum(total, 1), 0.0)
+    # np.mean over per-query python floats in the reference == pairwise mean over these arrays
+    return np.mean(rr.tolist()), hits / nq, np.mean(recalls.tolist())
+
+
+def compute_embedding_diversity(embeddings, device=None) -> float:
+    """``1 - mean pairwise cosine`` of one result set (``retrieval_diversity_compute.py:171-182``)."""
+    import torch
+    if embeddings is None or len(embeddings) < 2:
+        return 0.0
+    e = np.ascontiguousarray(embeddings, dtype=np.float32)
+    out = np.empty(1, dtype=np.float64)
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mmr_result_diversity(_lib.ptr(e), None, None, 1, e.shape[0], e.shape[1], 0, _lib.ptr(out), None,
+                                            dev, _lib.current_stream(dev)))
+    return float(out[0])
+
+
+def result_diversity_batch(cand_embs=None, cand_masks=None, counts=None, device=None):
+    """Batched diversity of B result sets: ``cand_embs`` (B, K, D) fp32 and/or ``cand_masks``
+    (B, K, words) uint64 -> ``(emb_div (B,), label_div (B,))`` fp64 (either may be ``None``)."""
+    import torch
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    b = int((cand_embs if cand_embs is not None else cand_masks).shape[0])
+    k = int((cand_embs if cand_embs is not None else cand_masks).shape[1])
+    e = np.ascontiguousarray(cand_embs, dtype=np.float32) if cand_embs is not None else None
+    m = np.ascontiguousarray(cand_masks, dtype=np.uint64) if cand_masks is not None else None
+    c = np.ascontiguousarray(counts, dtype=np.int32) if counts is not None else None
+    oe = np.empty(b, dtype=np.float64) if e is not None else None
+    ol = np.empty(b, dtype=np.float64) if m is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.mmr_result_diversity(_lib.ptr(e), _lib.ptr(m), _lib.ptr(c), b, k, e.shape[2] if e is not None else 0,
+                                            m.shape[2] if m is not None else 0, _lib.ptr(oe), _lib.ptr(ol), dev,
+                                            _lib.current_stream(dev)))
+    return oe, ol
+
+
+def compute_label_diversity_from_labels(labels_list, device=None) -> float:
+    """``unique labels / avg per-item label count`` (``retrieval_diversity_compute.py:184-194``)."""
+    if not labels_list:
+        return 0.0
+    names = sorted({l for lab in labels_list for l in lab})
+    if not names:
+        return 0.0
+    idx = {nm: i for i, nm in enumerate(names)}
+    words = (len(names) + 63) // 64
+    m = np.zeros((1, len(labels_list), words), dtype=np.uint64)
+    for i, lab in enumerate(labels_list):
+        for l in set(lab):
+            m[0, i, idx[l] // 64] |= np.uint64(1) << np.uint64(idx[l] % 64)
+    _, ol = result_diversity_batch(None, m, None, device)
+    return float(ol[0])

@@ -50,6 +50,8 @@ SIGNATURES = {
     "mmr_rerank_combine": [_vp, _vp, _i32, _i32, _f64, _f64, _f64, _i32, _vp, _vp, _i32, _vp],
     "mmr_rerank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f64, _f64, _f64, _i32, _vp, _vp, _vp],
     "mmr_metrics": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
+    "mmr_first_relevant_rank": [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
+    "mmr_result_diversity": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "mmr_label_relevance": [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, _vp],
 }
 _RESTYPES = {"mmr_last_error": C.c_char_p, "mmr_launch_count": C.c_int64}

@@ -791,6 +791,66 @@ int mmr_metrics(const int64_t* retrieved, const int32_t* ret_count, int32_t q, i
   return cs.finish();
 }
 
+int mmr_first_relevant_rank(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, const uint64_t* q_masks,
+                            const uint64_t* g_masks, int32_t label_words, int64_t* out_rank, int64_t* out_total,
+                            void* stream_v) {
+  MMR_REQUIRE(ix != nullptr, "mmr_first_relevant_rank: index is NULL");
+  MMR_REQUIRE(b >= 0 && label_words >= 1, "mmr_first_relevant_rank: bad sizes");
+  MMR_REQUIRE(q_dtype == MMR_F32 || q_dtype == MMR_BF16, "mmr_first_relevant_rank: bad q_dtype");
+  if (b == 0) return MMR_OK;
+  MMR_REQUIRE(q && q_masks && g_masks && out_rank && out_total, "mmr_first_relevant_rank: NULL argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  DeviceGuard guard(ix->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  // queries -> storage dtype (rounded like mmr_search) -> fp32 padded + inverse norms
+  const void* d_q = nullptr;
+  MMR_TRY(stage_in(q, static_cast<size_t>(b) * ix->d * elem_size(q_dtype), ix->q_in, stream, &d_q));
+  MMR_TRY(ix->q_store.ensure(static_cast<size_t>(b) * ix->d_pad * elem_size(ix->dtype)));
+  MMR_TRY(ix->q_inv.ensure(static_cast<size_t>(b) * sizeof(float)));
+  MMR_TRY(launch_ingest(d_q, q_dtype, b, ix->d, ix->d, ix->q_store.p, ix->dtype, ix->d_pad, ix->q_inv.as<float>(),
+                        stream));
+  const float* q_f32 = ix->q_store.as<float>();
+  if (ix->dtype == MMR_BF16) {
+    MMR_TRY(ix->q_f32.ensure(static_cast<size_t>(b) * ix->d_pad * sizeof(float)));
+    MMR_TRY(ix->scratch.ensure(static_cast<size_t>(b) * sizeof(float)));
+    MMR_TRY(launch_ingest(ix->q_store.p, MMR_BF16, b, ix->d_pad, ix->d_pad, ix->q_f32.p, MMR_F32, ix->d_pad,
+                          ix->scratch.as<float>(), stream));
+    q_f32 = ix->q_f32.as<float>();
+  }
+  CallScope cs(stream);
+  const uint64_t *d_qm, *d_gm;
+  int64_t *d_rank, *d_total;
+  MMR_TRY(cs.in(q_masks, static_cast<size_t>(b) * label_words, &d_qm));
+  MMR_TRY(cs.in(g_masks, static_cast<size_t>(ix->n) * label_words, &d_gm));
+  MMR_TRY(cs.out(out_rank, static_cast<size_t>(b), &d_rank));
+  MMR_TRY(cs.out(out_total, static_cast<size_t>(b), &d_total));
+  MMR_TRY(launch_first_relevant_rank(ix->emb, ix->dtype, ix->inv_norm, ix->n, ix->d_pad, q_f32, ix->q_inv.as<float>(), b,
+                                     d_qm, d_gm, label_words, d_rank, d_total, stream));
+  return cs.finish();
+}
+
+int mmr_result_diversity(const float* emb, const uint64_t* label_masks, const int32_t* counts, int32_t b, int32_t k,
+                         int32_t d, int32_t label_words, double* out_emb_div, double* out_label_div, int32_t device,
+                         void* stream_v) {
+  MMR_REQUIRE(b >= 0 && k >= 0 && d >= 0 && label_words >= 0, "mmr_result_diversity: bad sizes");
+  if (b == 0) return MMR_OK;
+  MMR_REQUIRE((emb && out_emb_div) || (label_masks && out_label_div), "mmr_result_diversity: nothing to compute");
+  MMR_TRY(check_device(device, nullptr));
+  DeviceGuard guard(device);
+  CallScope cs(static_cast<cudaStream_t>(stream_v));
+  const float* d_e;
+  const uint64_t* d_m;
+  const int32_t* d_c;
+  double *d_oe, *d_ol;
+  MMR_TRY(cs.in(emb, static_cast<size_t>(b) * k * d, &d_e));
+  MMR_TRY(cs.in(label_masks, static_cast<size_t>(b) * k * label_words, &d_m));
+  MMR_TRY(cs.in(counts, static_cast<size_t>(b), &d_c));
+  MMR_TRY(cs.out(out_emb_div, static_cast<size_t>(b), &d_oe));
+  MMR_TRY(cs.out(out_label_div, static_cast<size_t>(b), &d_ol));
+  MMR_TRY(launch_diversity(d_e, d_m, d_c, b, k, d, label_words, d_oe, d_ol, cs.stream));
+  return cs.finish();
+}
+
 int mmr_label_relevance(const uint64_t* q_masks, int64_t nq, const uint64_t* g_masks, int64_t ng, int32_t label_words,
                         int32_t exclude_self, uint8_t* out_relevant, int32_t device, void* stream_v) {
   MMR_REQUIRE(nq >= 0 && ng >= 0 && label_words >= 1, "mmr_label_relevance: bad sizes");

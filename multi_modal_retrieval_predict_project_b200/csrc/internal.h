@@ -108,4 +108,12 @@ int launch_metrics(const int64_t* retrieved, const int32_t* ret_count, int q, in
 int launch_label_relevance(const uint64_t* q_masks, int64_t nq, const uint64_t* g_masks, int64_t ng,
                            int label_words, int exclude_self, uint8_t* out, cudaStream_t stream);
 
+// eval.cu
+int launch_first_relevant_rank(const void* emb, int dtype_store, const float* inv_norm, int64_t n, int d_pad,
+                               const float* q_f32, const float* q_inv, int b, const uint64_t* q_masks,
+                               const uint64_t* g_masks, int words, int64_t* out_rank, int64_t* out_total,
+                               cudaStream_t stream);
+int launch_diversity(const float* emb, const uint64_t* masks, const int32_t* counts, int b, int k, int d, int words,
+                     double* out_emb_div, double* out_label_div, cudaStream_t stream);
+
 }  // namespace mmr

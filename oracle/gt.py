@@ -48,3 +48,27 @@ def compute_ranking_metrics(query_embs, gallery_embs, query_labels, gallery_labe
         total = int(rel.sum())
         recalls.append(int(rel[idxs[:k]].sum()) / total if total > 0 else 0.0)
     return np.mean(rr), hits / sim.shape[0], np.mean(recalls)
+
+
+def compute_embedding_diversity(embeddings) -> float:
+    """``retrieval_diversity_compute.py:171-182``: 1 - mean pairwise cosine (rows normalised with the
+    norm clipped at 1e-8; mean over the strict upper triangle; 0.0 for fewer than 2 items)."""
+    if embeddings is None or len(embeddings) < 2:
+        return 0.0
+    norms = np.linalg.norm(embeddings, axis=1, keepdims=True).clip(min=1e-8)
+    normed = embeddings / norms
+    sim = np.dot(normed, normed.T)
+    triu = np.triu_indices(sim.shape[0], k=1)
+    return float(1.0 - float(np.mean(sim[triu])))
+
+
+def compute_label_diversity_from_labels(labels_list) -> float:
+    """``retrieval_diversity_compute.py:184-194``: |union of labels| / mean label count over the items
+    that have labels; 0.0 when there are none."""
+    if not labels_list:
+        return 0.0
+    all_labels = set(l for lab in labels_list for l in lab)
+    sizes = [len(lab) for lab in labels_list if len(lab) > 0]
+    if not sizes:
+        return 0.0
+    return float(len(all_labels) / float(np.mean(sizes)))

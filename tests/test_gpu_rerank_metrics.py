@@ -207,3 +207,30 @@ def test_device_native_metrics_cfg5_style():
         rels = [rel[indptr[i]:indptr[i + 1]].tolist() for i in range(nq)]
         assert np.array_equal(got, om.per_query_table(rets, rels, kk))
         assert got[:, 0].sum() > 0
+
+
+def test_diversity_matches_reference_golden():
+    from multi_modal_retrieval_predict_project_b200.Evaluate import (compute_embedding_diversity,
+                                                                  compute_label_diversity_from_labels)
+    gold = json.load(open(GOLDEN / "diversity.json"))
+    for c in gold:
+        e = np.array(c["emb"], dtype=np.float32).reshape(len(c["emb"]), -1) if c["emb"] else np.zeros((0, 4), np.float32)
+        assert np.isclose(compute_embedding_diversity(e), c["emb_div"], rtol=0, atol=2e-6)
+        assert compute_label_diversity_from_labels(c["labels"]) == c["label_div"]
+
+
+def test_compute_ranking_metrics_large_gallery_vs_oracle():
+    """Full-ranking metrics beyond K = 1024: the rank of the first relevant item comes from the
+    two-sweep device reduction, not from a top-K list."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    from multi_modal_retrieval_predict_project_b200.Evaluate import compute_ranking_metrics
+    n, nq, d, L = 3000, 40, 96, 30
+    g = synth.make_embeddings(n, d, seed=61, clustered=True)
+    q = synth.make_embeddings(nq, d, seed=62, clustered=True)
+    gl = synth.make_labels(n, L, p=0.004, seed=63)       # sparse labels: first relevant rank is often deep
+    ql = synth.make_labels(nq, L, p=0.05, seed=64)
+    ql[3] = 0                                            # a query with no labels: rank None, recall 0
+    for k in (1, 10):
+        got = compute_ranking_metrics(q, g, ql, gl, k=k)
+        want = ogt.compute_ranking_metrics(q, g, ql, gl, k=k)
+        assert np.isclose(got[0], want[0], rtol=1e-9) and got[1] == want[1] and np.isclose(got[2], want[2], rtol=1e-9)

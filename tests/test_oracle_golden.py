@@ -149,3 +149,11 @@ def test_oracle_against_live_reference(tmp_path):
             assert om.average_precision(r, l, k) == ref.metrics.average_precision(r, l, k)
             assert om.ndcg_at_k(r, l, k) == ref.metrics.ndcg_at_k(r, l, k)
     assert om.mean_reciprocal_rank(ret, rel) == ref.metrics.mean_reciprocal_rank(ret, rel)
+
+
+def test_diversity_matches_reference():
+    gold = json.load(open(GOLDEN / "diversity.json"))
+    for c in gold:
+        e = np.array(c["emb"], dtype=np.float32).reshape(len(c["emb"]), -1) if c["emb"] else np.zeros((0, 4), np.float32)
+        assert np.isclose(ogt.compute_embedding_diversity(e), c["emb_div"], rtol=0, atol=1e-7)
+        assert ogt.compute_label_diversity_from_labels(c["labels"]) == c["label_div"]
