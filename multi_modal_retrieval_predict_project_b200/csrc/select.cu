@@ -186,7 +186,12 @@ select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = src.count(q);
   const int64_t chunk_base = static_cast<int64_t>(blockIdx.y) * 4096;
-  {
+  if (chunk_base + static_cast<int64_t>(warp) * 512 >= total) {  // nothing in this warp's slice
+    for (int i = lane; i < 128; i += 32) {
+      lvl2[warp * 128 + i] = 0ull;
+      lvl2_idx[warp * 128 + i] = -1;
+    }
+  } else {
     uint64_t key[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
