@@ -7,7 +7,8 @@
 Metric (BASELINE.json): queries/s for top-100 cosine + rerank over a 10M x 512 bf16 gallery.
 One "step" = one batch of queries through search -> top-K -> rerank.  At N > 1 the gallery is
 row-sharded over the ranks (strong scaling: total rows fixed), each rank searches its shard, then
-NCCL all-gather + on-device K-way merge + rerank.  Also reported on rank 0 at N = 1: the batch-1
+NCCL all-gather + on-device K-way merge + rerank (split by query across the ranks) + all-gather
+of the (ids, scores) slices.  Also reported on rank 0 at N = 1: the batch-1
 top-10 p50 latency (HBM-scan regime) and the CPU baseline.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -265,9 +266,9 @@ def main():
     def step(q):
         if reranker is None:
             return searcher.search(q, k)
-        rows, _scores, order, sc = searcher.search_rerank(reranker, q, k, q_rec, topk=k)  # record index == global row
         # what the reference's retrieve(..., reranker=...) returns: reranked ids + combined scores
-        return torch.gather(rows, 1, order.long()), sc[:, :, 0].contiguous()
+        # (record index == global row); at N > 1 the merge + rerank are split across ranks by query
+        return searcher.retrieve_reranked(reranker, q, k, q_rec, topk=k)
 
     def barrier():
         if world > 1:

@@ -123,6 +123,20 @@ int mmr_merge_topk_strided(const float* scores, const int64_t* rows, int32_t n_l
                            float* out_scores, int64_t* out_rows, int32_t* out_src, int32_t device,
                            void* stream);
 
+/* Payload carried through a merge (device pointers): out[q][i] = payload[list * list_stride +
+ * q * k_in + j] for the source position out_src[q][i] = list * k_in + j of mmr_merge_topk*, 0 where
+ * the slot is empty.  Used for the per-candidate embedding cosine each rank computed before the
+ * exchange (Retrieval/reranker.py:298 evaluated by the rank that owns the row). */
+int mmr_gather_payload(const float* payload, int64_t list_stride, const int32_t* src, int32_t b, int32_t k_in,
+                       int32_t k_out, float* out, int32_t device, void* stream);
+
+/* The (ids, scores) pair DLSRetrievalEngine.retrieve returns after a rerank
+ * (Retrieval/retrieval.py:257-269): rows (b, k) candidate ids, order (b, keep) and scores4
+ * (b, keep, 4) as written by mmr_rerank* -> out_rows (b, keep) ids in reranked order (-1 where
+ * order < 0) and out_final (b, keep) combined scores.  Device pointers. */
+int mmr_apply_order(const int64_t* rows, const int32_t* order, const double* scores4, int32_t b, int32_t k,
+                    int32_t keep, int64_t* out_rows, double* out_final, int32_t device, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Rerank.  Replaces Reranker.rerank (Retrieval/reranker.py:240-333).
  * Tables (built once, Reranker.__init__/_load_kg :29-129): per record `label_words` uint64

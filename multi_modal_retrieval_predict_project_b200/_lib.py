@@ -42,6 +42,8 @@ SIGNATURES = {
     "mmr_search": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "mmr_merge_topk": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp],
     "mmr_merge_topk_strided": [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp],
+    "mmr_gather_payload": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
+    "mmr_apply_order": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "mmr_candidate_cosine": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "mmr_rerank_with_cos": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _i32, _vp, _vp, _i32, _vp],
     "mmr_rerank_tables_create": [C.POINTER(_vp), _vp, _i32, _vp, _i32, _i64, _i32, _vp],

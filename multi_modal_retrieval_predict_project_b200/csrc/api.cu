@@ -485,7 +485,8 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
                              g_share_tau ? ix->tau_pub.as<uint32_t>() : nullptr, stream));
     if (ev1) MMR_CUDA_TRY(cudaEventRecord(ev1, stream));
     MMR_TRY(launch_select_var(ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), b, gp.n_lists, gp.cap, k_eff, k,
-                              ix->row_offset, d_excl, d_scores, d_rows, stream));
+                              ix->row_offset, d_excl, g_share_tau ? ix->tau_pub.as<uint32_t>() : nullptr,
+                              gp.m_tiles * 128, d_scores, d_rows, stream));
   } else {
     const float* q_f32 = nullptr;
     if (ix->dtype == MMR_F32) {
@@ -555,6 +556,31 @@ int mmr_merge_topk(const float* scores, const int64_t* rows, int32_t n_lists, in
   const int64_t per_list = static_cast<int64_t>(b) * k_in;
   return mmr_merge_topk_strided(scores, rows, n_lists, b, k_in, per_list, per_list, k_out, out_scores, out_rows,
                                 out_src, device, stream_v);
+}
+
+int mmr_gather_payload(const float* payload, int64_t list_stride, const int32_t* src, int32_t b, int32_t k_in,
+                       int32_t k_out, float* out, int32_t device, void* stream_v) {
+  MMR_REQUIRE(b >= 0 && k_in >= 1 && k_out >= 1, "mmr_gather_payload: bad sizes");
+  if (b == 0) return MMR_OK;
+  MMR_REQUIRE(payload && src && out, "mmr_gather_payload: NULL argument");
+  if (!(is_device_ptr(payload) && is_device_ptr(src) && is_device_ptr(out)))
+    return fail(MMR_EINVAL, "mmr_gather_payload: device pointers only");
+  MMR_TRY(check_device(device, nullptr));
+  DeviceGuard guard(device);
+  return launch_gather_payload(payload, list_stride, src, b, k_in, k_out, out, static_cast<cudaStream_t>(stream_v));
+}
+
+int mmr_apply_order(const int64_t* rows, const int32_t* order, const double* scores4, int32_t b, int32_t k,
+                    int32_t keep, int64_t* out_rows, double* out_final, int32_t device, void* stream_v) {
+  MMR_REQUIRE(b >= 0 && k >= 1 && keep >= 1 && keep <= k, "mmr_apply_order: bad sizes");
+  if (b == 0) return MMR_OK;
+  MMR_REQUIRE(rows && order && scores4 && out_rows && out_final, "mmr_apply_order: NULL argument");
+  if (!(is_device_ptr(rows) && is_device_ptr(order) && is_device_ptr(scores4) && is_device_ptr(out_rows) &&
+        is_device_ptr(out_final)))
+    return fail(MMR_EINVAL, "mmr_apply_order: device pointers only");
+  MMR_TRY(check_device(device, nullptr));
+  DeviceGuard guard(device);
+  return launch_apply_order(rows, order, scores4, b, k, keep, out_rows, out_final, static_cast<cudaStream_t>(stream_v));
 }
 
 int mmr_rerank_tables_create(mmr_rerank_tables** out, const uint64_t* label_masks, int32_t label_words,

@@ -70,6 +70,12 @@ int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, in
                        int64_t scores_list_stride, int64_t rows_list_stride, int k_out, float* out_scores,
                        int64_t* out_rows, int32_t* out_src, cudaStream_t stream);
 
+// select.cu: payload gather through a merge's source positions; reranked ids + combined score.
+int launch_gather_payload(const float* payload, int64_t list_stride, const int32_t* src, int b, int k_in, int k_out,
+                          float* out, cudaStream_t stream);
+int launch_apply_order(const int64_t* rows, const int32_t* order, const double* scores4, int b, int k, int keep,
+                       int64_t* out_rows, double* out_final, cudaStream_t stream);
+
 // gemm_topk.cu: tcgen05 GEMM + fused top-K (bf16 storage).
 struct GemmPlan {
   int m_tiles;          // query tiles of 128
@@ -87,8 +93,8 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
                      const float* q_inv, int b, int k, const int64_t* exclude_local, const GemmPlan& plan,
                      uint64_t* cand, int32_t* counts, uint32_t* tau_pub, cudaStream_t stream);
 int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int per_part,
-                      int k_out, int64_t row_offset, const int64_t* exclude_local, float* out_scores,
-                      int64_t* out_rows, cudaStream_t stream);
+                      int k_out, int64_t row_offset, const int64_t* exclude_local, const uint32_t* tau_pub, int b_pad,
+                      float* out_scores, int64_t* out_rows, cudaStream_t stream);
 
 // rerank.cu
 int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pad, int64_t row_offset,

@@ -144,6 +144,199 @@ rerank_features_kernel(const T* __restrict__ emb, int64_t n, int d_pad, int64_t 
   }
 }
 
+// Vectorised variant for the hot configuration (bf16 gallery rows gathered by candidate row, or a
+// precomputed cosine): 128-bit loads of the candidate's embedding row and KG vector (a 512-d bf16
+// row is two fully coalesced 512 B requests per warp instead of sixteen 64 B ones).  The kernel is
+// latency-bound (a chain row id -> row address -> gather -> shuffle reduction per candidate), so:
+//   * the candidate row / record ids of the whole query are staged in shared memory up front,
+//   * every warp works on kCand candidates at once -- all their gathers are issued before the first
+//     reduction, and the shuffle reductions of the candidates interleave,
+//   * the query's embedding / KG vector live in shared memory in the lane-sliced order the gathers
+//     use (lane l owns elements (it*32 + l)*8 .. +8), which keeps registers free for loads in flight.
+// kIts = ceil(d_pad / 256) embedding slices per lane, kKIts = ceil(d_kg / 128) KG slices per lane.
+// Same formulas as the generic kernel (safe_cos: dot / (||a|| * ||b||)).
+constexpr int kCand = 2;
+constexpr int kVecMaxK = 1024;
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+template <int kIts, int kKIts>
+__global__ void __launch_bounds__(256)
+rerank_features_vec_kernel(const __nv_bfloat16* __restrict__ emb, int64_t n, int d_pad, int64_t row_offset,
+                           const uint64_t* __restrict__ label_masks, int label_words, const float* __restrict__ kg,
+                           int d_kg, int64_t n_rec, const float* __restrict__ q_emb,
+                           const int64_t* __restrict__ cand_rows, const int64_t* __restrict__ q_rec,
+                           const int64_t* __restrict__ cand_rec, const int32_t* __restrict__ cand_count, int k, int d,
+                           double* __restrict__ out_raw, uint8_t* __restrict__ owned,
+                           const float* __restrict__ emb_cos_in, float* __restrict__ cos_out) {
+  __shared__ __align__(16) float qs[kIts * 256];
+  __shared__ __align__(16) float qks[kKIts * 128];
+  extern __shared__ __align__(16) int64_t s_ids[];  // [k] local rows (-1 = not in this shard) | [k] record ids
+  int64_t* const s_row = s_ids;
+  int64_t* const s_rec = s_ids + k;
+  const int qi = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int count = cand_count != nullptr ? min(cand_count[qi], k) : k;
+  const int64_t qr = q_rec != nullptr ? q_rec[qi] : -1;
+  const bool q_known = qr >= 0 && qr < n_rec;
+  const float* qkg = (q_known && kg != nullptr) ? kg + qr * d_kg : nullptr;
+  const uint64_t* qmask = (q_known && label_masks != nullptr) ? label_masks + qr * label_words : nullptr;
+  const bool need_emb = emb_cos_in == nullptr;
+  const bool feats = cos_out == nullptr;
+  const int nv = d_pad >> 3;  // 16-byte vectors per embedding row
+  const int nk = d_kg >> 2;   // float4 per KG row
+  const int64_t base = static_cast<int64_t>(qi) * k;
+
+  for (int i = threadIdx.x; i < kIts * 256; i += blockDim.x)
+    qs[i] = (need_emb && i < d) ? q_emb[static_cast<int64_t>(qi) * d + i] : 0.f;
+  for (int i = threadIdx.x; i < kKIts * 128; i += blockDim.x) qks[i] = (qkg != nullptr && i < d_kg) ? qkg[i] : 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    int64_t local = -1;
+    if (need_emb && j < count) {
+      local = cand_rows[base + j] - row_offset;
+      if (local < 0 || local >= n) local = -1;
+    }
+    s_row[j] = local;
+    const int64_t cr = (feats && cand_rec != nullptr && j < count) ? cand_rec[base + j] : -1;
+    s_rec[j] = (cr >= 0 && cr < n_rec) ? cr : -1;
+  }
+  __syncthreads();
+  float qss = 0.f, qkss = 0.f;
+#pragma unroll
+  for (int it = 0; it < kIts; ++it) {
+    const float4 a = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8);
+    const float4 c = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8 + 4);
+    qss = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, qss))));
+    qss = fmaf(c.x, c.x, fmaf(c.y, c.y, fmaf(c.z, c.z, fmaf(c.w, c.w, qss))));
+  }
+#pragma unroll
+  for (int it = 0; it < kKIts; ++it) {
+    const float4 a = *reinterpret_cast<const float4*>(qks + (it * 32 + lane) * 4);
+    qkss = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, qkss))));
+  }
+  qss = warp_sum(qss);
+  qkss = warp_sum(qkss);
+
+  for (int j0 = warp * kCand; j0 < k; j0 += nwarps * kCand) {
+    // ---- issue every gather of this warp's kCand candidates before the first reduction ----
+    uint4 x[kCand][kIts];
+    float4 y[kCand][kKIts];
+    uint64_t cmask[kCand];
+    bool have[kCand], do_kg[kCand], known[kCand];
+#pragma unroll
+    for (int c = 0; c < kCand; ++c) {
+      const int j = j0 + c;
+      const bool live = j < count;
+      const int64_t local = live ? s_row[j] : -1;
+      const int64_t cr = live ? s_rec[j] : -1;
+      have[c] = local >= 0;
+      known[c] = cr >= 0;
+      do_kg[c] = feats && qkg != nullptr && known[c];
+      const uint4* ce = reinterpret_cast<const uint4*>(emb + (have[c] ? local : 0) * d_pad);
+#pragma unroll
+      for (int it = 0; it < kIts; ++it) {
+        const int u = it * 32 + lane;
+        x[c][it] = (need_emb && have[c] && u < nv) ? __ldg(ce + u) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      const float4* ck = reinterpret_cast<const float4*>(kg + (do_kg[c] ? cr : 0) * d_kg);
+#pragma unroll
+      for (int it = 0; it < kKIts; ++it) {
+        const int u = it * 32 + lane;
+        y[c][it] = (do_kg[c] && u < nk) ? __ldg(ck + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      cmask[c] = (feats && label_masks != nullptr && known[c] && lane < label_words)
+                     ? label_masks[cr * label_words + lane] : 0ull;
+    }
+    // ---- reduce ----
+    float dot[kCand], css[kCand], kdot[kCand], kss[kCand];
+    int inter[kCand], uni[kCand];
+#pragma unroll
+    for (int c = 0; c < kCand; ++c) {
+      dot[c] = css[c] = kdot[c] = kss[c] = 0.f;
+      inter[c] = uni[c] = 0;
+    }
+#pragma unroll
+    for (int it = 0; it < kIts; ++it) {
+      const float4 qa = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8);
+      const float4 qb = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8 + 4);
+      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+      for (int c = 0; c < kCand; ++c) {
+        const uint32_t w[4] = {x[c][it].x, x[c][it].y, x[c][it].z, x[c][it].w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float lo = bf16_lo(w[h]), hi = bf16_hi(w[h]);
+          dot[c] = fmaf(lo, qv[2 * h], dot[c]);
+          css[c] = fmaf(lo, lo, css[c]);
+          dot[c] = fmaf(hi, qv[2 * h + 1], dot[c]);
+          css[c] = fmaf(hi, hi, css[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kKIts; ++it) {
+      const float4 qa = *reinterpret_cast<const float4*>(qks + (it * 32 + lane) * 4);
+#pragma unroll
+      for (int c = 0; c < kCand; ++c) {
+        const float4 v = y[c][it];
+        kdot[c] = fmaf(v.x, qa.x, fmaf(v.y, qa.y, fmaf(v.z, qa.z, fmaf(v.w, qa.w, kdot[c]))));
+        kss[c] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, kss[c]))));
+      }
+    }
+    if (feats && label_masks != nullptr) {
+      // label words beyond the first 32 (never the case for the 43-label table) go through the loop
+      const uint64_t a0 = (qmask != nullptr && lane < label_words) ? qmask[lane] : 0ull;
+#pragma unroll
+      for (int c = 0; c < kCand; ++c) {
+        inter[c] = __popcll(a0 & cmask[c]);
+        uni[c] = __popcll(a0 | cmask[c]);
+        for (int w = lane + 32; w < label_words; w += 32) {
+          const uint64_t a = qmask != nullptr ? qmask[w] : 0ull;
+          const uint64_t bb = known[c] ? label_masks[s_rec[min(j0 + c, k - 1)] * label_words + w] : 0ull;
+          inter[c] += __popcll(a & bb);
+          uni[c] += __popcll(a | bb);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < kCand; ++c) {
+        dot[c] += __shfl_xor_sync(0xffffffffu, dot[c], o);
+        css[c] += __shfl_xor_sync(0xffffffffu, css[c], o);
+        kdot[c] += __shfl_xor_sync(0xffffffffu, kdot[c], o);
+        kss[c] += __shfl_xor_sync(0xffffffffu, kss[c], o);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kCand; ++c) {
+      const int j = j0 + c;
+      if (j >= k) continue;
+      const int64_t at = base + j;
+      if (feats && label_masks != nullptr) {
+        inter[c] = __reduce_add_sync(0xffffffffu, inter[c]);
+        uni[c] = __reduce_add_sync(0xffffffffu, uni[c]);
+      }
+      if (lane != 0) continue;
+      const bool live = j < count;
+      const float e = !live ? 0.f : (need_emb ? (have[c] ? safe_cos_finish(dot[c], qss, css[c]) : 0.f) : emb_cos_in[at]);
+      if (!feats) {
+        cos_out[at] = e;
+      } else if (!live) {
+        out_raw[at * 3 + 0] = 0.0; out_raw[at * 3 + 1] = 0.0; out_raw[at * 3 + 2] = 0.0;
+      } else {
+        out_raw[at * 3 + 0] = static_cast<double>(e);
+        out_raw[at * 3 + 1] = uni[c] == 0 ? 0.0 : static_cast<double>(inter[c]) / static_cast<double>(uni[c]);
+        out_raw[at * 3 + 2] = static_cast<double>(do_kg[c] ? safe_cos_finish(kdot[c], qkss, kss[c]) : 0.f);
+      }
+      if (owned != nullptr) owned[at] = (live && have[c]) ? 1 : 0;
+    }
+  }
+}
+
 // One CTA per query.  dynamic smem: 4 * k doubles (final, emb_n, lab_n, kg_n).
 __global__ void __launch_bounds__(256)
 rerank_combine_kernel(const double* __restrict__ raw, const int32_t* __restrict__ cand_count, int k, double alpha,
@@ -226,6 +419,31 @@ int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pa
   if (b == 0 || k == 0) return MMR_OK;
   if (emb_cos_in == nullptr && cand_emb == nullptr && (emb == nullptr || cand_rows == nullptr))
     return fail(MMR_EINVAL, "Please provide candidate_embs or an index with candidate rows.");
+  // vectorised path: gathered bf16 rows (or a precomputed cosine), 16-byte aligned tables
+  const bool emb_vec_ok = emb_cos_in != nullptr ||
+                          (cand_emb == nullptr && dtype_store == MMR_BF16 && d_pad <= 1024 &&
+                           (reinterpret_cast<uintptr_t>(emb) & 15u) == 0);
+  const bool kg_vec_ok = kg == nullptr || (d_kg % 4 == 0 && d_kg <= 512 && (reinterpret_cast<uintptr_t>(kg) & 15u) == 0);
+  if (emb_vec_ok && kg_vec_ok && k <= kVecMaxK) {
+    const __nv_bfloat16* e16 = static_cast<const __nv_bfloat16*>(emb);
+    const int its = emb_cos_in != nullptr ? 1 : (d_pad + 255) / 256;
+    const int kits = kg == nullptr ? 1 : (d_kg + 127) / 128;
+    const size_t smem = static_cast<size_t>(2) * k * sizeof(int64_t);
+#define MMR_RERANK_VEC(ITS, KITS)                                                                                  \
+  rerank_features_vec_kernel<ITS, KITS><<<b, 256, smem, stream>>>(                                                 \
+      e16, n, d_pad, row_offset, label_masks, label_words, kg, d_kg, n_rec, q_emb, cand_rows, q_rec, cand_rec,     \
+      cand_count, k, d, out_raw, owned, emb_cos_in, cos_out)
+    if (its <= 1 && kits <= 3) {
+      MMR_RERANK_VEC(1, 3);
+    } else if (its <= 2 && kits <= 3) {
+      MMR_RERANK_VEC(2, 3);
+    } else {
+      MMR_RERANK_VEC(4, 4);
+    }
+#undef MMR_RERANK_VEC
+    MMR_LAUNCHED();
+    return MMR_OK;
+  }
   if (dtype_store == MMR_BF16 && cand_emb == nullptr) {
     rerank_features_kernel<__nv_bfloat16><<<b, 128, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(emb), n, d_pad, row_offset, label_masks, label_words, kg, d_kg, n_rec,

@@ -174,30 +174,119 @@ __device__ __forceinline__ void warp_bitonic_sort_desc_kv(uint64_t* s, int32_t* 
 // grid = (queries, chunks): chunk c selects among candidates [c * 4096, (c + 1) * 4096).  With
 // `stage_keys` != nullptr the (<= 128, zero padded) surviving keys go to stage_keys[q][c][128] for a
 // second pass instead of being decoded into scores / rows.
-template <typename Source>
+//
+// Pruning bound: the GEMM kernel publishes, per (list, query), a lower bound of the list's r-th best
+// score with r * n_lists >= k (gemm_topk.cu); when every list has published, the union holds >= k
+// candidates >= g = min over lists, so everything below g is dropped before any selection work.
+// When at most kRankCap candidates survive (typically 150-300 of 1800), the CTA ranks them by
+// counting (each thread counts the keys larger than its own: keys are unique, so the count IS the
+// output position) -- no radix descent and no sort.
+struct NoBound {
+  __device__ __forceinline__ uint32_t get(int, int) const { return 0u; }
+};
+struct TauBound {  // tau_pub[list][b_pad] of ordered-u32 scores, 0 = not published
+  const uint32_t* tau_pub;
+  int n_lists, b_pad;
+  __device__ __forceinline__ uint32_t get(int q, int lane) const {
+    if (tau_pub == nullptr) return 0u;
+    uint32_t g = 0xFFFFFFFFu;
+    for (int p = lane; p < n_lists; p += 32) {
+      const uint32_t v = __ldcg(tau_pub + static_cast<int64_t>(p) * b_pad + q);
+      g = v < g ? v : g;
+    }
+    return __reduce_min_sync(0xffffffffu, g);
+  }
+};
+constexpr int kRankCap = 512;
+
+template <typename Source, typename Bound>
 __global__ void __launch_bounds__(256)
-select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict__ out_scores,
+select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, float* __restrict__ out_scores,
                    int64_t* __restrict__ out_rows, int32_t* __restrict__ out_src, uint64_t* __restrict__ stage_keys) {
   __shared__ __align__(16) uint64_t lvl2[8 * 128];
   __shared__ int32_t lvl2_idx[8 * 128];
   __shared__ __align__(16) uint64_t fin[128];
   __shared__ int32_t fin_idx[128];
+  __shared__ int s_count;
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = src.count(q);
   const int64_t chunk_base = static_cast<int64_t>(blockIdx.y) * 4096;
-  if (chunk_base + static_cast<int64_t>(warp) * 512 >= total) {  // nothing in this warp's slice
+  const uint64_t gkey = static_cast<uint64_t>(bound.get(q, lane)) << 32;  // keys below are out of the top-k
+  const bool empty_slice = chunk_base + static_cast<int64_t>(warp) * 512 >= total;
+  uint64_t key[16];
+  int mine = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int64_t i = chunk_base + static_cast<int64_t>(warp) * 512 + e * 32 + lane;
+    uint64_t kk = (!empty_slice && i < total) ? src.get(q, i) : 0ull;
+    kk = kk < gkey ? 0ull : kk;
+    key[e] = kk;
+    mine += kk != 0ull ? 1 : 0;
+  }
+  if (stage_keys == nullptr) {
+    // ---- rank-by-counting path for small survivor sets ----
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const int wsum = __reduce_add_sync(0xffffffffu, mine);
+    int wbase = 0;
+    if (lane == 0 && wsum > 0) wbase = atomicAdd(&s_count, wsum);
+    __syncthreads();
+    const int m = s_count;
+    if (m <= kRankCap) {
+      // compact the survivors into lvl2 (keys) / lvl2_idx (source index); order is irrelevant
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int pos = wbase + incl - mine;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (key[e] != 0ull) {
+          lvl2[pos] = key[e];
+          lvl2_idx[pos] = warp * 512 + e * 32 + lane;
+          ++pos;
+        }
+      }
+      __syncthreads();
+      const uint64_t k0 = static_cast<int>(threadIdx.x) < m ? lvl2[threadIdx.x] : 0ull;
+      const uint64_t k1 = static_cast<int>(threadIdx.x) + 256 < m ? lvl2[threadIdx.x + 256] : 0ull;
+      int r0 = 0, r1 = 0;
+      for (int i = 0; i < m; ++i) {
+        const uint64_t kk = lvl2[i];
+        r0 += kk > k0 ? 1 : 0;
+        r1 += kk > k1 ? 1 : 0;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t k64 = h == 0 ? k0 : k1;
+        const int r = h == 0 ? r0 : r1;
+        if (k64 != 0ull && r < k_out) {
+          const int64_t o = static_cast<int64_t>(q) * k_out + r;
+          out_scores[o] = key_score(k64);
+          out_rows[o] = row_offset + static_cast<int64_t>(key_row(k64));
+          if (out_src != nullptr) out_src[o] = lvl2_idx[threadIdx.x + h * 256];
+        }
+      }
+      for (int i = m + threadIdx.x; i < k_out; i += blockDim.x) {  // fewer candidates than k_out
+        const int64_t o = static_cast<int64_t>(q) * k_out + i;
+        out_scores[o] = -INFINITY;
+        out_rows[o] = -1;
+        if (out_src != nullptr) out_src[o] = -1;
+      }
+      return;
+    }
+    __syncthreads();  // lvl2 is reused below
+  }
+  if (empty_slice) {  // nothing in this warp's slice
     for (int i = lane; i < 128; i += 32) {
       lvl2[warp * 128 + i] = 0ull;
       lvl2_idx[warp * 128 + i] = -1;
     }
   } else {
-    uint64_t key[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int64_t i = chunk_base + static_cast<int64_t>(warp) * 512 + e * 32 + lane;
-      key[e] = i < total ? src.get(q, i) : 0ull;
-    }
     const uint64_t thr = warp_topk_threshold<16>(key, k_out);
     warp_write_survivors<16>(key, thr, lvl2 + warp * 128, lvl2_idx + warp * 128, 128, lane,
                              [&](int e) { return warp * 512 + e * 32 + lane; });
@@ -232,12 +321,38 @@ select_fast_kernel(Source src, int k_out, int64_t row_offset, float* __restrict_
   }
 }
 
-template <typename Source>
+// payload carried through a merge: out[q][i] = payload[list * stride + q * k_in + j] for the source
+// position src[q][i] = list * k_in + j reported by the merge (0 where src < 0)
+__global__ void gather_payload_kernel(const float* __restrict__ payload, int64_t list_stride,
+                                      const int32_t* __restrict__ src, int64_t total, int k_in, int k_out,
+                                      float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int s = src[i];
+  const int64_t q = i / k_out;
+  out[i] = s < 0 ? 0.f : payload[static_cast<int64_t>(s / k_in) * list_stride + q * k_in + (s % k_in)];
+}
+
+// what retrieve(..., reranker=...) returns (Retrieval/retrieval.py:257-269): candidate ids in the
+// reranked order + the combined score
+__global__ void apply_order_kernel(const int64_t* __restrict__ rows, const int32_t* __restrict__ order,
+                                   const double* __restrict__ scores4, int64_t total, int k, int keep,
+                                   int64_t* __restrict__ out_rows, double* __restrict__ out_final) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int o = order[i];
+  const int64_t q = i / keep;
+  out_rows[i] = o < 0 ? -1 : rows[q * k + o];
+  out_final[i] = scores4[i * 4];
+}
+
+template <typename Source, typename Bound = NoBound>
 int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_offset, float* out_scores,
-                  int64_t* out_rows, int32_t* out_src, cudaStream_t stream) {
+                  int64_t* out_rows, int32_t* out_src, cudaStream_t stream, Bound bound = Bound()) {
   if (b == 0 || k_out == 0) return MMR_OK;
   if (k_out <= 128 && per_query <= 4096) {
-    select_fast_kernel<Source><<<b, 256, 0, stream>>>(src, k_out, row_offset, out_scores, out_rows, out_src, nullptr);
+    select_fast_kernel<Source, Bound><<<b, 256, 0, stream>>>(src, bound, k_out, row_offset, out_scores, out_rows,
+                                                             out_src, nullptr);
     MMR_LAUNCHED();
     return MMR_OK;
   }
@@ -247,12 +362,12 @@ int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_o
     uint64_t* stage = nullptr;
     MMR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&stage), static_cast<size_t>(b) * chunks * 128 * sizeof(uint64_t),
                                  stream));
-    select_fast_kernel<Source><<<dim3(b, chunks), 256, 0, stream>>>(src, k_out, row_offset, nullptr, nullptr, nullptr,
-                                                                   stage);
+    select_fast_kernel<Source, Bound><<<dim3(b, chunks), 256, 0, stream>>>(src, bound, k_out, row_offset, nullptr,
+                                                                          nullptr, nullptr, stage);
     count_launch();
     KeySourceFlat flat{stage, static_cast<int64_t>(chunks) * 128};
-    select_fast_kernel<KeySourceFlat><<<b, 256, 0, stream>>>(flat, k_out, row_offset, out_scores, out_rows, nullptr,
-                                                            nullptr);
+    select_fast_kernel<KeySourceFlat, NoBound><<<b, 256, 0, stream>>>(flat, NoBound(), k_out, row_offset, out_scores,
+                                                                     out_rows, nullptr, nullptr);
     count_launch();
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(stage, stream);
@@ -288,11 +403,32 @@ int launch_select_keys(const uint64_t* keys, int b, int64_t keys_per_query, int 
 }
 
 int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int per_part,
-                      int k_out, int64_t row_offset, const int64_t* exclude_local, float* out_scores,
-                      int64_t* out_rows, cudaStream_t stream) {
+                      int k_out, int64_t row_offset, const int64_t* exclude_local, const uint32_t* tau_pub, int b_pad,
+                      float* out_scores, int64_t* out_rows, cudaStream_t stream) {
   KeySourceVar src{reinterpret_cast<const uint2*>(cand), counts, n_parts, cap, per_part, exclude_local};
+  TauBound bound{tau_pub, n_parts, b_pad};
   return launch_select(src, b, static_cast<int64_t>(n_parts) * per_part, k_out, row_offset, out_scores, out_rows,
-                       nullptr, stream);
+                       nullptr, stream, bound);
+}
+
+int launch_gather_payload(const float* payload, int64_t list_stride, const int32_t* src, int b, int k_in, int k_out,
+                          float* out, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(b) * k_out;
+  if (total == 0) return MMR_OK;
+  gather_payload_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(payload, list_stride, src, total,
+                                                                                        k_in, k_out, out);
+  MMR_LAUNCHED();
+  return MMR_OK;
+}
+
+int launch_apply_order(const int64_t* rows, const int32_t* order, const double* scores4, int b, int k, int keep,
+                       int64_t* out_rows, double* out_final, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(b) * keep;
+  if (total == 0) return MMR_OK;
+  apply_order_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(rows, order, scores4, total, k,
+                                                                                     keep, out_rows, out_final);
+  MMR_LAUNCHED();
+  return MMR_OK;
 }
 
 int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in,

@@ -70,21 +70,16 @@ class ShardedSearcher:
         dist.all_gather_into_tensor(self._gr.view(self.world * b, K), rows.contiguous(), group=self.group)
         return self._merge(self._gs, self._gr, K)
 
-    def search_rerank(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
-        """The whole sharded step with ONE collective.  Every rank: local top-K, the fp32 embedding
-        cosine of its own K candidates (all rows are local), then a single NCCL all-gather of one
-        blob per rank ``[scores f32 | cosines f32 | rows i64]``; the strided on-device merge reads
-        the gathered blobs in place and reports where each winner came from, the cosines follow
-        through that index, and label/KG features come from the replicated tables.  The record index
-        of a candidate is its global row id.  Returns ``(rows, scores, order, rerank_scores)``."""
+    # ------------------------------------------------------------------------------------------
+    # one-collective step: local top-K + local cosines -> ONE all-gather of a per-rank blob
+    # [scores f32 | cosines f32 | rows i64] -> strided merge straight out of the gathered buffer
+    # ------------------------------------------------------------------------------------------
+    def _local_blob(self, reranker, queries, K, algo):
+        """Per-rank part of the step: search the shard, cosine of the local candidates, all-gather."""
         import torch
         import torch.distributed as dist
         eng = self.engine
         b = int(queries.shape[0])
-        if self.world == 1:
-            rows, scores = eng.search(queries, K, algo=algo)
-            order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
-            return rows, scores, order, sc
         bk = b * K
         dev = queries.device
         if getattr(self, "_blob", None) is None or self._blob.numel() != bk * 16:
@@ -96,23 +91,92 @@ class ShardedSearcher:
         eng.search(queries, K, algo=algo, out_rows=rows_v, out_scores=scores_v)
         reranker.candidate_cosine_device(eng, queries, rows_v, out=cos_v)
         dist.all_gather_into_tensor(self._gblob, self._blob, group=self.group)
-        gf = self._gblob.view(torch.float32)            # per-rank stride: 4*bk floats
-        gi = self._gblob.view(torch.int64)              # per-rank stride: 2*bk int64, rows start at +bk
-        out_s = torch.empty((b, K), dtype=torch.float32, device=dev)
-        out_r = torch.empty((b, K), dtype=torch.int64, device=dev)
-        src = torch.empty((b, K), dtype=torch.int32, device=dev)
+        return self._gblob
+
+    def _merge_slice(self, gblob, b, K, q_lo, q_hi):
+        """Merge queries [q_lo, q_hi) out of the gathered blobs -> (rows, scores, cosines)."""
+        import torch
+        bk = b * K
+        dev = gblob.device
+        n = q_hi - q_lo
+        gf = gblob.view(torch.float32)            # per-rank stride: 4*bk floats
+        gi = gblob.view(torch.int64)              # per-rank stride: 2*bk int64, rows start at +bk
+        out_s = torch.empty((n, K), dtype=torch.float32, device=dev)
+        out_r = torch.empty((n, K), dtype=torch.int64, device=dev)
+        src = torch.empty((n, K), dtype=torch.int32, device=dev)
+        cos = torch.empty((n, K), dtype=torch.float32, device=dev)
         lib = _lib.load()
         d = dev.index or 0
+        off = q_lo * K
         with torch.cuda.device(d):
-            _lib.check(lib.mmr_merge_topk_strided(gf.data_ptr(), gi.data_ptr() + bk * 8, self.world, b, K, 4 * bk,
-                                                  2 * bk, K, _lib.ptr(out_s), _lib.ptr(out_r), _lib.ptr(src), d,
-                                                  _lib.current_stream(d)))
-        srcl = src.long().clamp_(min=0)
-        qoff = torch.arange(b, device=dev, dtype=torch.int64).unsqueeze(1) * K
-        cos_idx = (srcl // K) * (4 * bk) + bk + qoff + (srcl % K)
-        cos = gf[cos_idx.reshape(-1)].view(b, K).contiguous()
+            st = _lib.current_stream(d)
+            _lib.check(lib.mmr_merge_topk_strided(gf.data_ptr() + off * 4, gi.data_ptr() + (bk + off) * 8, self.world,
+                                                  n, K, 4 * bk, 2 * bk, K, _lib.ptr(out_s), _lib.ptr(out_r),
+                                                  _lib.ptr(src), d, st))
+            _lib.check(lib.mmr_gather_payload(gf.data_ptr() + (bk + off) * 4, 4 * bk, _lib.ptr(src), n, K, K,
+                                              _lib.ptr(cos), d, st))
+        return out_r, out_s, cos
+
+    def search_rerank(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
+        """The whole sharded step with ONE collective.  Every rank: local top-K, the fp32 embedding
+        cosine of its own K candidates (all rows are local), then a single NCCL all-gather of one
+        blob per rank ``[scores f32 | cosines f32 | rows i64]``; the strided on-device merge reads
+        the gathered blobs in place and reports where each winner came from, the cosines follow
+        through that index, and label/KG features come from the replicated tables.  The record index
+        of a candidate is its global row id.  Returns ``(rows, scores, order, rerank_scores)``."""
+        eng = self.engine
+        b = int(queries.shape[0])
+        if self.world == 1:
+            rows, scores = eng.search(queries, K, algo=algo)
+            order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
+            return rows, scores, order, sc
+        gblob = self._local_blob(reranker, queries, K, algo)
+        out_r, out_s, cos = self._merge_slice(gblob, b, K, 0, b)
         order, sc = reranker.rerank_with_cos_device(cos, q_rec, out_r, topk)
         return out_r, out_s, order, sc
+
+    def retrieve_reranked(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
+        """What ``retrieve(q, K, reranker=..., query_id=...)`` returns (Retrieval/retrieval.py:257-269)
+        for a batch: ``(ids (B, keep) int64 in reranked order, combined scores (B, keep) fp64)``.
+        Sharded: after the blob all-gather every rank merges and reranks only ITS slice of the
+        queries (the post-processing is split G ways instead of replicated), then the (ids, scores)
+        slices are all-gathered so that every rank ends with the full result."""
+        import torch
+        import torch.distributed as dist
+        eng = self.engine
+        b = int(queries.shape[0])
+        keep = topk if 0 < topk < K else K
+        dev = queries.device
+        d = dev.index or 0
+        lib = _lib.load()
+        if self.world == 1:
+            rows, _scores = eng.search(queries, K, algo=algo)
+            order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
+            ids = torch.empty((b, keep), dtype=torch.int64, device=dev)
+            fin = torch.empty((b, keep), dtype=torch.float64, device=dev)
+            with torch.cuda.device(d):
+                _lib.check(lib.mmr_apply_order(_lib.ptr(rows), _lib.ptr(order), _lib.ptr(sc), b, K, keep, _lib.ptr(ids),
+                                               _lib.ptr(fin), d, _lib.current_stream(d)))
+            return ids, fin
+        gblob = self._local_blob(reranker, queries, K, algo)
+        rank = dist.get_rank(self.group)
+        per = (b + self.world - 1) // self.world
+        q_lo, q_hi = min(b, rank * per), min(b, (rank + 1) * per)
+        if getattr(self, "_fin", None) is None or self._fin[0].shape != (self.world * per, keep):
+            self._fin = (torch.empty((self.world * per, keep), dtype=torch.int64, device=dev),
+                         torch.empty((self.world * per, keep), dtype=torch.float64, device=dev),
+                         torch.full((per, keep), -1, dtype=torch.int64, device=dev),
+                         torch.zeros((per, keep), dtype=torch.float64, device=dev))
+        all_ids, all_fin, my_ids, my_fin = self._fin
+        if q_hi > q_lo:
+            out_r, _out_s, cos = self._merge_slice(gblob, b, K, q_lo, q_hi)
+            order, sc = reranker.rerank_with_cos_device(cos, q_rec[q_lo:q_hi], out_r, topk)
+            with torch.cuda.device(d):
+                _lib.check(lib.mmr_apply_order(_lib.ptr(out_r), _lib.ptr(order), _lib.ptr(sc), q_hi - q_lo, K, keep,
+                                               _lib.ptr(my_ids), _lib.ptr(my_fin), d, _lib.current_stream(d)))
+        dist.all_gather_into_tensor(all_ids, my_ids, group=self.group)
+        dist.all_gather_into_tensor(all_fin, my_fin, group=self.group)
+        return all_ids[:b], all_fin[:b]
 
     def rerank(self, reranker, q_embs, rows, q_rec, cand_rec, topk: int = 0):
         """Rerank merged global candidates: the label/KG tables are replicated, the candidate

@@ -1,4 +1,7 @@
-"""Diagnostic: CUDA-event timing of the phases of the sharded step (torchrun --nproc-per-node N)."""
+"""Diagnostic: CUDA-event timing of the phases of the sharded step (torchrun --nproc-per-node N):
+search | local cosine | blob all-gather | merge+payload of this rank's query slice | rerank |
+apply order | result all-gathers, next to the whole retrieve_reranked() call and the replicated
+search_rerank() it replaced."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -9,7 +12,7 @@ from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher, 
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
-rows, dim, b, k = int(os.environ.get("ROWS", 10_000_000)), 512, 4096, 100
+rows, dim, b, k = int(os.environ.get("ROWS", 10_000_000)), 512, int(os.environ.get("BATCH", 4096)), 100
 lo, hi = shard_bounds(rows, world, rank)
 g = bench.gen_rows(lo, hi, dim, bench.SEED, dev, torch.bfloat16)
 eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=lr, row_offset=lo, borrow=True, keep_host=False)
@@ -18,14 +21,19 @@ q = torch.randn((b, dim), device=dev).to(torch.bfloat16).float()
 masks = bench.gen_masks(0, rows + b, dev); kg = bench.gen_rows(0, rows + b, 300, bench.SEED + 700000, dev, torch.float32, normalize=True)
 rer = Reranker.from_tables(masks, kg, device=lr); del masks, kg
 q_rec = torch.arange(rows, rows + b, device=dev)
-for _ in range(3): s.search_rerank(rer, q, k, q_rec, topk=k)
+for _ in range(3):
+    s.retrieve_reranked(rer, q, k, q_rec, topk=k); s.search_rerank(rer, q, k, q_rec, topk=k)
 torch.cuda.synchronize()
-names = ["search", "cosine", "allgather", "merge", "glue", "rerank"]
-tot = {n: 0.0 for n in names}
 lib = _lib.load()
-for it in range(5):
+names = ["search", "cosine", "allgather_blob", "merge_slice", "rerank_slice", "apply_order", "allgather_result"]
+tot = {n: 0.0 for n in names}
+whole = {"retrieve_reranked": 0.0, "search_rerank(replicated)": 0.0}
+per = (b + world - 1) // world
+q_lo, q_hi = min(b, rank * per), min(b, (rank + 1) * per)
+iters = 5
+for it in range(iters):
     dist.barrier(); torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
     bk = b * k
     f = s._blob[: bk * 8].view(torch.float32)
     scores_v, cos_v = f[:bk].view(b, k), f[bk:].view(b, k)
@@ -34,15 +42,22 @@ for it in range(5):
     eng.search(q, k, out_rows=rows_v, out_scores=scores_v); ev[1].record()
     rer.candidate_cosine_device(eng, q, rows_v, out=cos_v); ev[2].record()
     dist.all_gather_into_tensor(s._gblob, s._blob); ev[3].record()
-    gf = s._gblob.view(torch.float32); gi = s._gblob.view(torch.int64)
-    out_s = torch.empty((b, k), dtype=torch.float32, device=dev); out_r = torch.empty((b, k), dtype=torch.int64, device=dev)
-    src = torch.empty((b, k), dtype=torch.int32, device=dev)
-    _lib.check(lib.mmr_merge_topk_strided(gf.data_ptr(), gi.data_ptr() + bk * 8, world, b, k, 4 * bk, 2 * bk, k, _lib.ptr(out_s), _lib.ptr(out_r), _lib.ptr(src), lr, _lib.current_stream(lr))); ev[4].record()
-    srcl = src.long().clamp_(min=0)
-    qoff = torch.arange(b, device=dev, dtype=torch.int64).unsqueeze(1) * k
-    cos = gf[((srcl // k) * (4 * bk) + bk + qoff + (srcl % k)).reshape(-1)].view(b, k).contiguous(); ev[5].record()
-    order, sc = rer.rerank_with_cos_device(cos, q_rec, out_r, k); ev[6].record()
+    out_r, out_s, cos = s._merge_slice(s._gblob, b, k, q_lo, q_hi); ev[4].record()
+    order, sc = rer.rerank_with_cos_device(cos, q_rec[q_lo:q_hi], out_r, k); ev[5].record()
+    all_ids, all_fin, my_ids, my_fin = s._fin
+    _lib.check(lib.mmr_apply_order(_lib.ptr(out_r), _lib.ptr(order), _lib.ptr(sc), q_hi - q_lo, k, k, _lib.ptr(my_ids),
+                                   _lib.ptr(my_fin), lr, _lib.current_stream(lr))); ev[6].record()
+    dist.all_gather_into_tensor(all_ids, my_ids); dist.all_gather_into_tensor(all_fin, my_fin); ev[7].record()
     torch.cuda.synchronize()
     for i, n in enumerate(names): tot[n] += ev[i].elapsed_time(ev[i + 1])
-if rank == 0: print({n: round(v / 5, 3) for n, v in tot.items()})
+    for name, fn in (("retrieve_reranked", lambda: s.retrieve_reranked(rer, q, k, q_rec, topk=k)),
+                     ("search_rerank(replicated)", lambda: s.search_rerank(rer, q, k, q_rec, topk=k))):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        whole[name] += e0.elapsed_time(e1)
+if rank == 0:
+    print({"world": world, "rows": rows, "batch": b})
+    print({n: round(v / iters, 3) for n, v in tot.items()})
+    print({n: round(v / iters, 3) for n, v in whole.items()})
 dist.destroy_process_group()

@@ -34,9 +34,11 @@ def _worker(rank, world, port, out_dir):
     q_rec = torch.arange(n, n + b, device="cuda")
     order, sc = s.rerank(rer, qd, rows, q_rec, rows.clone(), topk=20)
     rows2, scores2, order2, sc2 = s.search_rerank(rer, qd, k, q_rec, topk=20)       # one-collective path
+    ids3, fin3 = s.retrieve_reranked(rer, qd, k, q_rec, topk=20)                      # query-split post-processing
     torch.cuda.synchronize()
     assert torch.equal(rows2, rows) and torch.equal(scores2, scores)
     assert torch.equal(order2, order) and torch.equal(sc2, sc)
+    assert torch.equal(ids3, torch.gather(rows, 1, order.long())) and torch.equal(fin3, sc[:, :, 0])
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), rows=rows.cpu().numpy(), scores=scores.cpu().numpy(),
              order=order.cpu().numpy(), sc=sc.cpu().numpy())
     if rank == 0:  # single-shard reference on the same device
