@@ -67,6 +67,9 @@ struct __align__(16) SmemAux {
 // Shared-memory plan.  kResident (d_pad <= 512): the 128-query tile stays in shared memory for
 // the whole CTA (num_kc x 16 KiB) and only gallery chunks stream through the stage ring, which
 // removes a third of the L2->SM and TMA->smem traffic.  Otherwise both operands stream per chunk.
+// kPair (cta_group::2): two CTAs on the SMs of one TPC work on 256 queries x the same gallery tile.
+// Each CTA stages only HALF of the gallery tile (128 rows) and the pair's MMA reads both halves, so
+// the L2 -> SM and shared-memory traffic per FLOP of the gallery operand halves.
 struct SmemPlan {
   bool resident;
   int num_stages;
@@ -74,13 +77,14 @@ struct SmemPlan {
   int q_bytes;
   size_t total;
 };
-inline SmemPlan plan_smem(int d_pad) {
+inline SmemPlan plan_smem(int d_pad, bool pair) {
   SmemPlan p;
   const int num_kc = d_pad / kBlockK;
-  p.resident = static_cast<size_t>(num_kc) * kABytes + 2 * static_cast<size_t>(kBBytes) + sizeof(SmemAux) <=
+  const int b_bytes = pair ? kBBytes / 2 : kBBytes;
+  p.resident = static_cast<size_t>(num_kc) * kABytes + 2 * static_cast<size_t>(b_bytes) + sizeof(SmemAux) <=
                static_cast<size_t>(kMaxSmemOptin);
   p.q_bytes = p.resident ? num_kc * kABytes : 0;
-  p.stage_bytes = p.resident ? kBBytes : kABytes + kBBytes;
+  p.stage_bytes = p.resident ? b_bytes : kABytes + b_bytes;
   int st = static_cast<int>((kMaxSmemOptin - p.q_bytes - static_cast<int>(sizeof(SmemAux))) / p.stage_bytes);
   p.num_stages = st > kMaxStages ? kMaxStages : st;
   p.total = static_cast<size_t>(p.q_bytes) + static_cast<size_t>(p.num_stages) * p.stage_bytes + sizeof(SmemAux);
@@ -128,6 +132,34 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to a barrier that may
+// live in the peer CTA (`bar_cluster` is a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* smem, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -155,6 +187,27 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// pair variants: one instruction drives the tensor cores of both SMs (M = 256: 128 rows per CTA, each
+// CTA supplies its own A tile and half of the B tile); commit arrives on the barrier at the same
+// shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -331,7 +384,7 @@ __device__ __forceinline__ float pre_threshold(float tau, float qinv) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kResident>
+template <bool kResident, bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                  const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
@@ -344,7 +397,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
   const int num_kc = d_pad / kBlockK;
-  constexpr int kStageBytes = kResident ? kBBytes : kABytes + kBBytes;
+  constexpr int kBStage = kPair ? kBBytes / 2 : kBBytes;  // gallery bytes this CTA stages per chunk
+  constexpr int kStageBytes = kResident ? kBStage : kABytes + kBStage;
   uint8_t* const smem_q = smem_raw;                                             // resident query chunks
   uint8_t* const smem = smem_raw + (kResident ? num_kc * kABytes : 0);          // stage ring
   SmemAux* aux = reinterpret_cast<SmemAux*>(smem + static_cast<size_t>(num_stages) * kStageBytes);
@@ -355,11 +409,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   // query tile are co-resident (they exchange pruning thresholds through tau_pub) and the CTAs that
   // stream the SAME gallery part sit on neighbouring SMs and run in step, so the part is fetched
   // from HBM once and served to the others from L2.
+  // Pair mode: the scheduling unit is the 2-CTA cluster (two consecutive query tiles, same part);
+  // m_group / m_tiles then count PAIRS of query tiles.  A pair whose second tile lies beyond the batch
+  // still runs both CTAs (the query TMA zero-fills, no query row is valid).
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const int unit = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int m_units = kPair ? (m_tiles + 1) / 2 : m_tiles;
   const int per_group = n_parts * m_group;
-  const int rem = static_cast<int>(blockIdx.x) % per_group;
-  const int m_tile = (static_cast<int>(blockIdx.x) / per_group) * m_group + rem % m_group;
+  const int rem = unit % per_group;
+  const int m_unit = (unit / per_group) * m_group + rem % m_group;
   const int part = rem / m_group;
-  if (m_tile >= m_tiles) return;  // padding CTAs of the last group (whole CTA exits before any barrier)
+  if (m_unit >= m_units) return;  // padding units of the last group (whole CTA / pair exits before any barrier)
+  const int m_tile = kPair ? m_unit * 2 + static_cast<int>(cta_rank) : m_unit;
+  const bool leader = cta_rank == 0u;
   const int tile_begin = part * tiles_per_part;
   const int tile_end = min(tile_begin + tiles_per_part, tiles_total);
   const int num_tiles = tile_end - tile_begin;
@@ -374,15 +436,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(&aux->q_full, 1);
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&aux->tmem_full[s], 1);
-      mbar_init(&aux->tmem_empty[s], kEpiThreads / 32);
+      mbar_init(&aux->tmem_empty[s], kPair ? 2 : 1);  // one arrival per epilogue warpgroup of each CTA
     }
     fence_barrier_init();
   }
-  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&aux->tmem_base)),
-                 "r"(static_cast<uint32_t>(kTmemCols))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  if (warp == 1) {  // TMEM allocation (whole warp; in pair mode the same warp of both CTAs), address in smem
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&aux->tmem_base)),
+                   "r"(static_cast<uint32_t>(kTmemCols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&aux->tmem_base)),
+                   "r"(static_cast<uint32_t>(kTmemCols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -394,20 +464,40 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
+        // pair mode: both CTAs load into their own shared memory, but every byte is credited to the
+        // LEADER's barriers (the leader issues the MMAs); the leader alone posts the expected bytes
         if (kResident) {  // the query tile is loaded once and reused for every gallery tile
-          mbar_expect_tx(&aux->q_full, static_cast<uint32_t>(num_kc * kABytes));
-          for (int kc = 0; kc < num_kc; ++kc)
-            tma_load_2d(&tmap_q, &aux->q_full, smem_q + static_cast<size_t>(kc) * kABytes, kc * kBlockK,
-                        m_tile * kBlockM);
+          if (leader) mbar_expect_tx(&aux->q_full, static_cast<uint32_t>((kPair ? 2 : 1) * num_kc * kABytes));
+          const uint32_t qbar = kPair ? mapa_rank(smem_u32(&aux->q_full), 0u) : 0u;
+          for (int kc = 0; kc < num_kc; ++kc) {
+            if (kPair)
+              tma_load_2d_pair(&tmap_q, qbar, smem_q + static_cast<size_t>(kc) * kABytes, kc * kBlockK,
+                               m_tile * kBlockM);
+            else
+              tma_load_2d(&tmap_q, &aux->q_full, smem_q + static_cast<size_t>(kc) * kABytes, kc * kBlockK,
+                          m_tile * kBlockM);
+          }
         }
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < num_tiles; ++t) {
-          const int n0 = (tile_begin + t) * kBlockN;
+          // pair mode: this CTA stages gallery rows [n0, n0 + 128) of the pair's 256-row tile
+          const int n0 = (tile_begin + t) * kBlockN + (kPair ? static_cast<int>(cta_rank) * (kBlockN / 2) : 0);
           for (int kc = 0; kc < num_kc; ++kc) {
             mbar_wait(&aux->empty[stage], phase ^ 1u);
             uint8_t* sa = smem + static_cast<size_t>(stage) * kStageBytes;
             uint8_t* sb = kResident ? sa : sa + kABytes;
+            if (kPair) {
+              if (leader) mbar_expect_tx(&aux->full[stage], 2 * kStageBytes);
+              const uint32_t fbar = mapa_rank(smem_u32(&aux->full[stage]), 0u);
+              if (!kResident) tma_load_2d_pair(&tmap_q, fbar, sa, kc * kBlockK, m_tile * kBlockM);
+              tma_load_2d_pair(&tmap_g, fbar, sb, kc * kBlockK, n0);
+              if (++stage == num_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+              continue;
+            }
             mbar_expect_tx(&aux->full[stage], kStageBytes);
             if (!kResident) tma_load_2d(&tmap_q, &aux->full[stage], sa, kc * kBlockK, m_tile * kBlockM);
             tma_load_2d(&tmap_g, &aux->full[stage], sb, kc * kBlockK, n0);
@@ -420,8 +510,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(kBlockM, kBlockN);
+      if (lane == 0 && leader) {  // pair mode: only the leader CTA issues (for both SMs)
+        constexpr uint32_t idesc = make_idesc(kPair ? 2 * kBlockM : kBlockM, kBlockN);
         int stage = 0;
         uint32_t phase = 0;
         if (kResident) mbar_wait(&aux->q_full, 0u);
@@ -442,16 +532,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
             for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
               // advance 16 bf16 = 32 bytes inside the 128-byte swizzle span: +2 in the (>>4) address field
-              umma_f16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc + static_cast<uint64_t>(kk * 2), idesc,
-                       (kc | kk) != 0 ? 1u : 0u);
+              if (kPair)
+                umma_f16_pair(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc + static_cast<uint64_t>(kk * 2),
+                              idesc, (kc | kk) != 0 ? 1u : 0u);
+              else
+                umma_f16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc + static_cast<uint64_t>(kk * 2), idesc,
+                         (kc | kk) != 0 ? 1u : 0u);
             }
-            umma_commit(&aux->empty[stage]);  // frees the smem stage when these MMAs retire
+            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+            if (kPair) umma_commit_pair(&aux->empty[stage]); else umma_commit(&aux->empty[stage]);
             if (++stage == num_stages) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          umma_commit(&aux->tmem_full[acc]);  // accumulator complete
+          // accumulator complete (each CTA of a pair holds its own 128 query rows of it)
+          if (kPair) umma_commit_pair(&aux->tmem_full[acc]); else umma_commit(&aux->tmem_full[acc]);
         }
       }
     }
@@ -602,7 +698,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       tc_fence_before();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // all 4 warps are done with TMEM stage + ginv
-      if (epi_tid == 0) mbar_arrive_n(&aux->tmem_empty[group], kEpiThreads / 32);
+      if (epi_tid == 0) {  // the MMA issuer (the leader CTA's in pair mode) may overwrite this stage
+        if (kPair)
+          mbar_arrive_cluster(mapa_rank(smem_u32(&aux->tmem_empty[group]), 0u));
+        else
+          mbar_arrive_n(&aux->tmem_empty[group], 1);
+      }
     }
     // final exact top-k per list so that select.cu merges short lists
     {
@@ -622,12 +723,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();  // pair: neither CTA leaves while the other may still touch it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(kTmemCols))
-                 : "memory");
+    if (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(kTmemCols))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(kTmemCols))
+                   : "memory");
   }
 }
 
@@ -675,16 +781,22 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
   if (d_pad % kBlockK != 0) return fail(MMR_EINVAL, "gemm: d_pad must be a multiple of 64");
   const int m_tiles = (b + kBlockM - 1) / kBlockM;
   const int64_t tiles_total = (n + kBlockN - 1) / kBlockN;
-  // pick the number of gallery parts so that m_tiles * parts fills whole waves of SMs
+  // CTA pairs (cta_group::2) whenever there are at least two query tiles; MMR_B200_GEMM_PAIR=0 disables
+  static const bool pair_env = std::getenv("MMR_B200_GEMM_PAIR") == nullptr || std::atoi(std::getenv("MMR_B200_GEMM_PAIR")) != 0;
+  const bool pair = pair_env && m_tiles >= 2;
+  const int ctas_per_unit = pair ? 2 : 1;
+  const int m_units = pair ? (m_tiles + 1) / 2 : m_tiles;   // scheduling units along the batch
+  const int slots = num_sms / ctas_per_unit;                // units resident at once
+  // pick the number of gallery parts so that m_units * parts fills whole waves of SMs
   int best_parts = 1;
   double best_eff = -1.0;
   for (int w = 1; w <= 8; ++w) {
-    int64_t parts = static_cast<int64_t>(w) * num_sms / m_tiles;
+    int64_t parts = static_cast<int64_t>(w) * slots / m_units;
     if (parts < 1) parts = 1;
     if (parts > tiles_total) parts = tiles_total;
-    const int64_t ctas = parts * m_tiles;
-    const int64_t waves = (ctas + num_sms - 1) / num_sms;
-    const double eff = static_cast<double>(ctas) / static_cast<double>(waves * num_sms);
+    const int64_t ctas = parts * m_units;
+    const int64_t waves = (ctas + slots - 1) / slots;
+    const double eff = static_cast<double>(ctas) / static_cast<double>(waves * slots);
     if (eff > best_eff + 0.02) {
       best_eff = eff;
       best_parts = static_cast<int>(parts);
@@ -699,10 +811,11 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
   plan->m_tiles = m_tiles;
   plan->n_parts = n_parts;
   plan->n_lists = n_parts * kEpiGroups;
-  {  // query tiles per wave: as many as fit next to all parts, at least 1
-    int g = num_sms / n_parts;
+  plan->pair = pair ? 1 : 0;
+  {  // query tiles (pairs of them in pair mode) per wave: as many as fit next to all parts, at least 1
+    int g = slots / n_parts;
     if (g < 1) g = 1;
-    if (g > m_tiles) g = m_tiles;
+    if (g > m_units) g = m_units;
     plan->m_group = g;
   }
   plan->tiles_per_part = tiles_per_part;
@@ -718,12 +831,15 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
                      const GemmPlan& plan, uint64_t* cand, int32_t* counts, uint32_t* tau_pub, cudaStream_t stream) {
   CUtensorMap tmap_q, tmap_g;
   MMR_TRY(make_tmap(&tmap_q, q_bf16, b, d_pad, kBlockM));
-  MMR_TRY(make_tmap(&tmap_g, emb_bf16, n, d_pad, kBlockN));
-  const SmemPlan sp = plan_smem(d_pad);
+  const bool pair = plan.pair != 0;
+  MMR_TRY(make_tmap(&tmap_g, emb_bf16, n, d_pad, pair ? kBlockN / 2 : kBlockN));
+  const SmemPlan sp = plan_smem(d_pad, pair);
   if (sp.num_stages < 2) return fail(MMR_EUNSUP, "gemm: embedding dimension too large for the shared-memory plan");
   const int tiles_total = static_cast<int>((n + kBlockN - 1) / kBlockN);
-  const int grid = ((plan.m_tiles + plan.m_group - 1) / plan.m_group) * plan.m_group * plan.n_parts;
-  auto kern = sp.resident ? gemm_topk_kernel<true> : gemm_topk_kernel<false>;
+  const int m_units = pair ? (plan.m_tiles + 1) / 2 : plan.m_tiles;
+  const int grid = ((m_units + plan.m_group - 1) / plan.m_group) * plan.m_group * plan.n_parts * (pair ? 2 : 1);
+  auto kern = pair ? (sp.resident ? gemm_topk_kernel<true, true> : gemm_topk_kernel<false, true>)
+                   : (sp.resident ? gemm_topk_kernel<true, false> : gemm_topk_kernel<false, false>);
   MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sp.total)));
   // threshold exchange: rank published per part and refresh period (in gallery tiles)
   // MMR_B200_GEMM_DEBUG bit 0: skip the epilogue's score processing (results are garbage) to
@@ -736,14 +852,26 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   // 1M x 2048/4096 (16 sharers): without the synchronous first compaction the sharers drift apart
   // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).  MMR_B200_EARLY_TILES overrides.
   static const int early_env = std::getenv("MMR_B200_EARLY_TILES") ? std::atoi(std::getenv("MMR_B200_EARLY_TILES")) : -1;
-  const int early_tiles = early_env >= 0 ? early_env : (plan.m_group <= 8 ? 8 : 0);
+  const int early_tiles = early_env >= 0 ? early_env : (plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0);
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
   MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));
-  kern<<<grid, kNumThreads, sp.total, stream>>>(tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap,
-                                                plan.m_tiles, plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total,
-                                                sp.num_stages, pub_rank, refresh, early_tiles, debug_flags,
-                                                reinterpret_cast<uint2*>(cand), counts, tau_pub);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = sp.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;  // the CTA pair is a 2-CTA cluster (one TPC)
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  uint2* cand2 = reinterpret_cast<uint2*>(cand);
+  MMR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap, plan.m_tiles,
+                                  plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total, sp.num_stages, pub_rank,
+                                  refresh, early_tiles, debug_flags, cand2, counts, tau_pub));
   MMR_LAUNCHED();
   return MMR_OK;
 }

@@ -79,7 +79,8 @@ int launch_apply_order(const int64_t* rows, const int32_t* order, const double* 
 // gemm_topk.cu: tcgen05 GEMM + fused top-K (bf16 storage).
 struct GemmPlan {
   int m_tiles;          // query tiles of 128
-  int m_group;          // query tiles scheduled together (one wave covers m_group x n_parts CTAs)
+  int pair;             // 1 = cta_group::2 (a 2-CTA cluster works on two query tiles x one gallery tile)
+  int m_group;          // query tiles (pairs in pair mode) scheduled together: one wave = m_group x n_parts units
   int n_parts;          // gallery parts (CTAs per query tile)
   int n_lists;          // candidate lists per query (parts x epilogue warpgroups)
   int tiles_per_part;   // gallery tiles of 256 rows per part
