@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(sp)
                 and os.path.getmtime(obj) >= headers_mtime):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", sp, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("NVCC_EXTRA", "").split(), "-c", sp, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

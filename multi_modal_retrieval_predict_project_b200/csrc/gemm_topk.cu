@@ -30,7 +30,9 @@
 // Roofline: tensor-core bound, 2 * b * n * d_pad FLOP per launch.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "internal.h"
 
@@ -391,7 +393,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  int k, int cap, int m_tiles, int m_group, int n_parts, int tiles_per_part, int tiles_total,
                  int num_stages,
                  int pub_rank, int refresh_tiles, int early_tiles, int debug_flags, uint2* __restrict__ cand,
-                 int32_t* __restrict__ counts, uint32_t* __restrict__ tau_pub) {
+                 int32_t* __restrict__ counts, uint32_t* __restrict__ tau_pub, unsigned long long* __restrict__ trace) {
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; the declaration requests it and the
   // kernel traps loudly if the runtime did not honour it (no slack bytes are budgeted).
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -621,6 +623,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       mbar_wait(&aux->tmem_full[group], acc_phase);
       tc_fence_after();
+#ifdef MMR_GEMM_TRACE  // diagnostic build only (scripts/trace_gemm.py): when did accumulator tile t become ready
+      if (trace != nullptr && epi_tid == 0 && (t < 40 || (group == 0 && (t & 31) == 0 && (t >> 5) < 23))) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        // slots 1..40: tiles 0..39 (both warpgroups); slots 41..: every 32nd tile from 32 on
+        trace[static_cast<size_t>(blockIdx.x) * 64 + (t < 40 ? 1 + t : 40 + (t >> 5))] = now;
+      }
+#endif
 #pragma unroll 1
       for (int c = 0; c < ((debug_flags & 1) ? 0 : kBlockN / 32); ++c) {
         uint32_t v[32];
@@ -869,10 +879,31 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   uint2* cand2 = reinterpret_cast<uint2*>(cand);
+  unsigned long long* trace = nullptr;
+#ifdef MMR_GEMM_TRACE
+  // MMR_B200_GEMM_TRACE=<file>: per-CTA tile timestamps, dumped after the launch (synchronises!)
+  static const char* trace_path = std::getenv("MMR_B200_GEMM_TRACE");
+  if (trace_path != nullptr) {
+    MMR_CUDA_TRY(cudaMalloc(&trace, static_cast<size_t>(grid) * 64 * sizeof(unsigned long long)));
+    MMR_CUDA_TRY(cudaMemsetAsync(trace, 0, static_cast<size_t>(grid) * 64 * sizeof(unsigned long long), stream));
+  }
+#endif
   MMR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap, plan.m_tiles,
                                   plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total, sp.num_stages, pub_rank,
-                                  refresh, early_tiles, debug_flags, cand2, counts, tau_pub));
+                                  refresh, early_tiles, debug_flags, cand2, counts, tau_pub, trace));
   MMR_LAUNCHED();
+#ifdef MMR_GEMM_TRACE
+  if (trace != nullptr) {
+    MMR_CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> h(static_cast<size_t>(grid) * 64);
+    MMR_CUDA_TRY(cudaMemcpy(h.data(), trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    if (FILE* f = std::fopen(trace_path, "wb")) {
+      std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+      std::fclose(f);
+    }
+  }
+#endif
   return MMR_OK;
 }
 

@@ -109,21 +109,46 @@ select_topk_kernel(Source src, int k_out, int sz, int keep, int64_t row_offset, 
 // survivors; warp 0 repeats the selection over the 8 x 128 survivors and bitonic-sorts the final
 // <= 128 keys.  ~10x cheaper than sorting 4096 keys with a CTA-wide bitonic network.
 // ---------------------------------------------------------------------------------------------
+// count(key >= T) == k threshold, MSB-first radix descent on the score word first and on the row
+// word only to break ties on the k-th score (see gemm_topk.cu: warp_rank_threshold)
 template <int E>
 __device__ __forceinline__ uint64_t warp_topk_threshold(const uint64_t (&key)[E], int k) {
-  uint64_t prefix = 0;
-  for (int bit = 63; bit >= 0; --bit) {
-    const uint64_t cand = prefix | (1ull << bit);
+  uint32_t prefix = 0;
+  bool exact = false;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = prefix | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) c += (key[e] >= cand) ? 1 : 0;
+    for (int e = 0; e < E; ++e) c += (static_cast<uint32_t>(key[e] >> 32) >= cand) ? 1 : 0;
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= k) {
       prefix = cand;
-      if (c == k) break;
+      if (c == k) {
+        exact = true;
+        break;
+      }
     }
   }
-  return prefix;  // 0 when fewer than k valid keys: everything non-zero survives
+  if (exact) return static_cast<uint64_t>(prefix) << 32;
+  int above = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) above += (static_cast<uint32_t>(key[e] >> 32) > prefix) ? 1 : 0;
+  above = __reduce_add_sync(0xffffffffu, above);
+  const int need = k - above;
+  uint32_t low = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = low | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      c += (static_cast<uint32_t>(key[e] >> 32) == prefix && static_cast<uint32_t>(key[e]) >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= need) {
+      low = cand;
+      if (c == need) break;
+    }
+  }
+  return (static_cast<uint64_t>(prefix) << 32) | low;  // 0 when fewer than k valid keys: everything non-zero survives
 }
 
 // survivors (key >= thr) of a warp's register-resident keys -> dst[0..cap), with the index each key

@@ -208,6 +208,21 @@ def test_gemm_other_dims(n, d, b, k):
     _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("n,d,b,k", [(9000, 512, 300, 100), (9000, 1024, 300, 10), (100, 64, 257, 20),
+                                     (129, 512, 385, 100), (70000, 512, 1500, 100)])
+def test_gemm_cta_pairs(n, d, b, k):
+    """cta_group::2 path (>= 2 query tiles): odd numbers of query tiles (the last pair runs a CTA with no
+    valid query), the streamed-Q pair variant (D = 1024), galleries smaller than one 256-row tile (the
+    peer CTA's half of the tile is entirely out of bounds) and a many-wave batch."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=83))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=84))
+    eng = _engine(g, dtype="bfloat16")
+    rows, scores = eng.search(q, k, algo="gemm")
+    want_rows, want_scores = osr.exact_topk(q, g, k)
+    _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+
+
 def test_gemm_duplicates_and_zero_rows():
     """Exact-score ties (duplicated gallery rows, reference Trainner/train.py:438-454 samples with
     replacement) resolve to ascending row id; zero rows / zero queries score exactly 0."""
