@@ -138,6 +138,42 @@ int mmr_apply_order(const int64_t* rows, const int32_t* order, const double* sco
                     int32_t keep, int64_t* out_rows, double* out_final, int32_t device, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Multi-GPU exchange over NVLink peer memory (gallery row-sharded, one process per GPU; the
+ * replacement for "concatenate every shard's candidates and argsort", i.e. the distributed form
+ * of Evaluate/retrieval_overlap.py:85,90).  Queries are split across the ranks; the owner of a
+ * query merges the G local top-K lists and reranks them.  No collective library call is on the
+ * data path: lists and results move with peer stores issued by the kernels themselves.
+ *   create    allocate this rank's region (sized for b_max queries, k_max results)
+ *   handle    CUDA IPC handle of the region (mmr_exchange_handle_bytes() bytes) -- exchange the
+ *             handles of all ranks out of band (torch.distributed all_gather) and pass them,
+ *             rank-major, to open
+ *   scatter   fused kernel: fp32 cosine of this rank's (b, k) local candidates (reranker.py:298)
+ *             + stores of {score, cosine, global row} into the owners' regions + signal
+ *   merge     wait for all ranks' lists of step `step`, merge this rank's query slice
+ *             [rank*ceil(b/G), ...) -> (n_local, k) scores / rows / cosines, best first
+ *   publish   store this rank's slice of the final (ids, combined scores) (n_local, keep) into
+ *             every rank's result buffer + signal
+ *   collect   wait for all slices; *ids / *fin point at the full (b, keep) result in this
+ *             rank's region (valid until step + 2 is scattered)
+ * `step` must increase by one per round on every rank (buffers alternate by its parity).
+ * ------------------------------------------------------------------------------------- */
+typedef struct mmr_exchange mmr_exchange;
+int mmr_exchange_create(mmr_exchange** out, int32_t rank, int32_t world, int32_t b_max, int32_t k_max,
+                        int32_t device);
+int mmr_exchange_handle_bytes(void);
+int mmr_exchange_handle(mmr_exchange* ex, void* handle_out);
+int mmr_exchange_open(mmr_exchange* ex, const void* handles);
+int mmr_exchange_destroy(mmr_exchange* ex);
+int mmr_exchange_scatter(mmr_exchange* ex, const mmr_index* index, const float* q_emb, const int64_t* rows,
+                         const float* scores, int32_t b, int32_t k, uint32_t step, void* stream);
+int mmr_exchange_merge(mmr_exchange* ex, int32_t b, int32_t k, uint32_t step, float* out_scores,
+                       int64_t* out_rows, float* out_cos, void* stream);
+int mmr_exchange_publish(mmr_exchange* ex, const int64_t* ids, const double* fin, int32_t b, int32_t keep,
+                         uint32_t step, void* stream);
+int mmr_exchange_collect(mmr_exchange* ex, int32_t b, int32_t keep, uint32_t step, const int64_t** ids,
+                         const double** fin, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Rerank.  Replaces Reranker.rerank (Retrieval/reranker.py:240-333).
  * Tables (built once, Reranker.__init__/_load_kg :29-129): per record `label_words` uint64
  * words of label bits (get_record_label_set :161-179) and a d_kg fp32 KG vector

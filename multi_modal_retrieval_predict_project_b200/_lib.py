@@ -44,6 +44,15 @@ SIGNATURES = {
     "mmr_merge_topk_strided": [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp],
     "mmr_gather_payload": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp],
     "mmr_apply_order": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+    "mmr_exchange_create": [C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32],
+    "mmr_exchange_handle_bytes": [],
+    "mmr_exchange_handle": [_vp, _vp],
+    "mmr_exchange_open": [_vp, _vp],
+    "mmr_exchange_destroy": [_vp],
+    "mmr_exchange_scatter": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, C.c_uint32, _vp],
+    "mmr_exchange_merge": [_vp, _i32, _i32, C.c_uint32, _vp, _vp, _vp, _vp],
+    "mmr_exchange_publish": [_vp, _vp, _vp, _i32, _i32, C.c_uint32, _vp],
+    "mmr_exchange_collect": [_vp, _i32, _i32, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), _vp],
     "mmr_candidate_cosine": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "mmr_rerank_with_cos": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _i32, _vp, _vp, _i32, _vp],
     "mmr_rerank_tables_create": [C.POINTER(_vp), _vp, _i32, _vp, _i32, _i64, _i32, _vp],
@@ -113,6 +122,22 @@ def ptr(x) -> Optional[int]:
     if isinstance(x, int):
         return x
     raise TypeError(f"cannot take the address of {type(x)!r}")
+
+
+class _DevMem:
+    """__cuda_array_interface__ view of library-owned device memory."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def as_cuda_tensor(ptr: int, shape, dtype, device: int):
+    """Zero-copy torch view of device memory owned by the library (valid as long as the owner says)."""
+    import torch
+    typestr = {torch.int64: "<i8", torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DevMem(ptr, shape, typestr), device=torch.device("cuda", device))
 
 
 def current_stream(device: int) -> int:

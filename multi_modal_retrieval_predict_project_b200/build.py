@@ -17,7 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libmmr_b200.so")
-SOURCES = ["api.cu", "ingest.cu", "scan_topk.cu", "select.cu", "gemm_topk.cu", "rerank.cu", "metrics.cu", "eval.cu"]
+SOURCES = ["api.cu", "ingest.cu", "scan_topk.cu", "select.cu", "gemm_topk.cu", "rerank.cu", "metrics.cu", "eval.cu",
+           "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

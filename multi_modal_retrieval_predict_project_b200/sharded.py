@@ -1,9 +1,16 @@
 """Row-sharded search across the GPUs of one NVSwitch box (one process per GPU).
 
 Gallery rows are split into contiguous shards; every rank searches its own
-shard (no data-path collective), then ONE exchange: an NCCL all-gather of the per-rank top-K
-``(score fp32, global row int64)`` lists over NVLink, followed by the on-device K-way merge
-(csrc/select.cu).  ``torch.distributed`` is plumbing only.
+shard (no data-path collective), then ONE exchange of the per-rank top-K ``(score fp32, global row
+int64)`` lists over NVLink, followed by the on-device K-way merge (csrc/select.cu).
+
+Two transports for the exchange:
+  * ``PeerExchange`` (default for ``retrieve_reranked``): the lists are written straight into the
+    owning rank's memory by the kernel that computes them (csrc/exchange.cu: CUDA-IPC peer mappings,
+    NVLink stores, flag signalling) -- no collective library call on the data path;
+  * NCCL ``all_gather_into_tensor`` (``search`` / ``search_rerank``, and the fallback when peer
+    mappings are unavailable).
+``torch.distributed`` is plumbing only (handle exchange, barriers).
 """
 from __future__ import annotations
 
@@ -42,15 +49,56 @@ def merge_topk(scores, rows, k_out: int, want_src: bool = False):
     return out_r, out_s
 
 
+class PeerExchange:
+    """This rank's exchange region + peer mappings of all other ranks' regions (csrc/exchange.cu).
+    The CUDA IPC handles are exchanged once through ``torch.distributed`` (any backend)."""
+
+    def __init__(self, device: int, b_max: int, k_max: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self._lib = _lib.load()
+        self.device = int(device)
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.b_max, self.k_max = int(b_max), int(k_max)
+        self.step = 0
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.mmr_exchange_create(C.byref(h), self.rank, self.world, self.b_max, self.k_max,
+                                                     self.device))
+            self._h = h
+            nbytes = self._lib.mmr_exchange_handle_bytes()
+            mine = C.create_string_buffer(nbytes)
+            _lib.check(self._lib.mmr_exchange_handle(self._h, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            blob = b"".join(handles)
+            _lib.check(self._lib.mmr_exchange_open(self._h, blob))
+        dist.barrier(group=group)  # every rank has mapped every region before anybody stores into one
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mmr_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedSearcher:
     """Per-rank shard + all-gather + merge.  ``engine`` holds this rank's rows (``row_offset`` set
     to the shard's first global row).  Works with any initialised ``torch.distributed`` process
     group whose backend supports CUDA tensors (NCCL); with world size 1 it is a pass-through."""
 
-    def __init__(self, engine, group=None, merge=None):
+    def __init__(self, engine, group=None, merge=None, use_peer: bool = True):
         import torch.distributed as dist
         self.engine = engine
         self.group = group
+        self.use_peer = use_peer
         self._merge = merge if merge is not None else merge_topk  # injectable for the CPU/gloo plumbing tests
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self._gs = self._gr = None
@@ -138,9 +186,12 @@ class ShardedSearcher:
     def retrieve_reranked(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
         """What ``retrieve(q, K, reranker=..., query_id=...)`` returns (Retrieval/retrieval.py:257-269)
         for a batch: ``(ids (B, keep) int64 in reranked order, combined scores (B, keep) fp64)``.
-        Sharded: after the blob all-gather every rank merges and reranks only ITS slice of the
-        queries (the post-processing is split G ways instead of replicated), then the (ids, scores)
-        slices are all-gathered so that every rank ends with the full result."""
+        Sharded: every rank merges and reranks only ITS slice of the queries (the post-processing is
+        split G ways instead of replicated) and every rank ends with the full result.  With the
+        peer exchange (default) the local lists and the result slices move with NVLink stores issued
+        by the kernels themselves (csrc/exchange.cu) and the returned tensors are views of this
+        rank's exchange region, valid until the call after next; otherwise one NCCL all-gather of
+        the per-rank blobs and two of the result slices."""
         import torch
         import torch.distributed as dist
         eng = self.engine
@@ -158,10 +209,44 @@ class ShardedSearcher:
                 _lib.check(lib.mmr_apply_order(_lib.ptr(rows), _lib.ptr(order), _lib.ptr(sc), b, K, keep, _lib.ptr(ids),
                                                _lib.ptr(fin), d, _lib.current_stream(d)))
             return ids, fin
-        gblob = self._local_blob(reranker, queries, K, algo)
         rank = dist.get_rank(self.group)
         per = (b + self.world - 1) // self.world
         q_lo, q_hi = min(b, rank * per), min(b, (rank + 1) * per)
+        nloc = q_hi - q_lo
+        px = self._peer_exchange(b, K, queries)
+        if px is not None:
+            # ---- NVLink peer-memory path: no collective call between search and result ----
+            import ctypes as C
+            if getattr(self, "_loc", None) is None or self._loc[0].shape != (b, K):
+                self._loc = (torch.empty((b, K), dtype=torch.int64, device=dev),
+                             torch.empty((b, K), dtype=torch.float32, device=dev))
+            rows_l, scores_l = self._loc
+            eng.search(queries, K, algo=algo, out_rows=rows_l, out_scores=scores_l)
+            px.step += 1
+            step = px.step
+            with torch.cuda.device(d):
+                st = _lib.current_stream(d)
+                _lib.check(lib.mmr_exchange_scatter(px._h, eng._handle, _lib.ptr(queries), _lib.ptr(rows_l),
+                                                    _lib.ptr(scores_l), b, K, step, st))
+                out_s = torch.empty((max(nloc, 1), K), dtype=torch.float32, device=dev)
+                out_r = torch.empty((max(nloc, 1), K), dtype=torch.int64, device=dev)
+                cos = torch.empty((max(nloc, 1), K), dtype=torch.float32, device=dev)
+                _lib.check(lib.mmr_exchange_merge(px._h, b, K, step, _lib.ptr(out_s), _lib.ptr(out_r), _lib.ptr(cos), st))
+                ids = fin = None
+                if nloc > 0:
+                    order, sc = reranker.rerank_with_cos_device(cos[:nloc], q_rec[q_lo:q_hi], out_r[:nloc], topk)
+                    ids = torch.empty((nloc, keep), dtype=torch.int64, device=dev)
+                    fin = torch.empty((nloc, keep), dtype=torch.float64, device=dev)
+                    _lib.check(lib.mmr_apply_order(_lib.ptr(out_r), _lib.ptr(order), _lib.ptr(sc), nloc, K, keep,
+                                                   _lib.ptr(ids), _lib.ptr(fin), d, st))
+                _lib.check(lib.mmr_exchange_publish(px._h, _lib.ptr(ids), _lib.ptr(fin), b, keep, step, st))
+                p_ids, p_fin = C.c_void_p(), C.c_void_p()
+                _lib.check(lib.mmr_exchange_collect(px._h, b, keep, step, C.byref(p_ids), C.byref(p_fin), st))
+            # the full (b, keep) result lives in this rank's exchange region until step + 2
+            return (_lib.as_cuda_tensor(p_ids.value, (b, keep), torch.int64, d),
+                    _lib.as_cuda_tensor(p_fin.value, (b, keep), torch.float64, d))
+        # ---- NCCL path ----
+        gblob = self._local_blob(reranker, queries, K, algo)
         if getattr(self, "_fin", None) is None or self._fin[0].shape != (self.world * per, keep):
             self._fin = (torch.empty((self.world * per, keep), dtype=torch.int64, device=dev),
                          torch.empty((self.world * per, keep), dtype=torch.float64, device=dev),
@@ -177,6 +262,23 @@ class ShardedSearcher:
         dist.all_gather_into_tensor(all_ids, my_ids, group=self.group)
         dist.all_gather_into_tensor(all_fin, my_fin, group=self.group)
         return all_ids[:b], all_fin[:b]
+
+    def _peer_exchange(self, b: int, K: int, queries):
+        """The NVLink peer-memory exchange for (b, K), created on first use (collective: every rank
+        calls with the same sizes).  ``use_peer=False`` or MMR_B200_NO_PEER=1 selects the NCCL path;
+        indexes the fused scatter kernel does not cover (fp32 storage, d > 1024) use NCCL as well."""
+        import os
+        if not self.use_peer or os.environ.get("MMR_B200_NO_PEER") == "1" or self.world > 16:
+            return None
+        if self.engine.dtype != "bfloat16" or int(queries.shape[1]) > 1024 or K > _lib.MAX_K:
+            return None
+        px = getattr(self, "_px", None)
+        if px is None or px.b_max < b or px.k_max < K:
+            if px is not None:
+                px.close()
+            self._px = px = PeerExchange(queries.device.index or 0, max(b, px.b_max if px else 0),
+                                         max(K, px.k_max if px else 0), group=self.group)
+        return px
 
     def rerank(self, reranker, q_embs, rows, q_rec, cand_rec, topk: int = 0):
         """Rerank merged global candidates: the label/KG tables are replicated, the candidate

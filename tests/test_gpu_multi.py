@@ -34,11 +34,25 @@ def _worker(rank, world, port, out_dir):
     q_rec = torch.arange(n, n + b, device="cuda")
     order, sc = s.rerank(rer, qd, rows, q_rec, rows.clone(), topk=20)
     rows2, scores2, order2, sc2 = s.search_rerank(rer, qd, k, q_rec, topk=20)       # one-collective path
-    ids3, fin3 = s.retrieve_reranked(rer, qd, k, q_rec, topk=20)                      # query-split post-processing
+    want_ids, want_fin = torch.gather(rows, 1, order.long()), sc[:, :, 0]
+    # query-split post-processing over NVLink peer memory (csrc/exchange.cu): several rounds so that
+    # both buffer parities are used, then other batch sizes / K (ragged last slice, re-created region)
+    for _ in range(3):
+        ids3, fin3 = s.retrieve_reranked(rer, qd, k, q_rec, topk=20)
+        torch.cuda.synchronize()
+        assert getattr(s, "_px", None) is not None, "peer exchange was not used"
+        assert torch.equal(ids3, want_ids) and torch.equal(fin3, want_fin)
+    s_nccl = ShardedSearcher(eng, use_peer=False)                                     # same step through NCCL
+    ids4, fin4 = s_nccl.retrieve_reranked(rer, qd, k, q_rec, topk=20)
     torch.cuda.synchronize()
     assert torch.equal(rows2, rows) and torch.equal(scores2, scores)
     assert torch.equal(order2, order) and torch.equal(sc2, sc)
-    assert torch.equal(ids3, torch.gather(rows, 1, order.long())) and torch.equal(fin3, sc[:, :, 0])
+    assert torch.equal(ids4, want_ids) and torch.equal(fin4, want_fin)
+    for bb, kk in ((33, 50), (1, 10), (70, 64)):
+        a_ids, a_fin = s.retrieve_reranked(rer, qd[:bb].contiguous(), kk, q_rec[:bb].contiguous(), topk=0)
+        b_ids, b_fin = s_nccl.retrieve_reranked(rer, qd[:bb].contiguous(), kk, q_rec[:bb].contiguous(), topk=0)
+        torch.cuda.synchronize()
+        assert torch.equal(a_ids, b_ids) and torch.equal(a_fin, b_fin), (bb, kk)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), rows=rows.cpu().numpy(), scores=scores.cpu().numpy(),
              order=order.cpu().numpy(), sc=sc.cpu().numpy())
     if rank == 0:  # single-shard reference on the same device
