@@ -263,6 +263,61 @@ class ShardedSearcher:
         dist.all_gather_into_tensor(all_fin, my_fin, group=self.group)
         return all_ids[:b], all_fin[:b]
 
+    def serve(self, reranker, host_batches, K: int, q_rec, topk: int = 0, algo: Optional[str] = None,
+              to_host: bool = True):
+        """Serving loop over HOST query batches: a generator that takes pinned host tensors ``(B, D)``
+        fp32 and yields, per batch, the host ``(ids (B, keep) int64, scores (B, keep) fp64)`` pair
+        that ``retrieve(..., reranker=...)`` returns.  Three streams keep the copies off the compute
+        path: the host->device copy of batch i + 1 and the device->host copy of batch i - 1 overlap
+        the search of batch i (results are yielded one batch late; the yielded pinned buffers are
+        reused two batches later).  ``to_host=False`` (ranks that do not hand results to a caller)
+        skips the device->host copy and yields the device tensors."""
+        import torch
+        dev = torch.device("cuda", self.engine.device)
+        s_cmp = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        qd, hout = [None, None], [None, None]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event(blocking=True) for _ in range(2)]
+        pending = None
+        for i, batch in enumerate(host_batches):
+            slot = i & 1
+            if qd[slot] is None or qd[slot].shape != batch.shape:
+                qd[slot] = torch.empty(batch.shape, dtype=torch.float32, device=dev)
+            if i >= 2:
+                s_in.wait_event(ev_cmp[slot])          # the search of batch i - 2 has consumed qd[slot]
+            with torch.cuda.stream(s_in):
+                qd[slot].copy_(batch, non_blocking=True)
+                ev_in[slot].record(s_in)
+            s_cmp.wait_event(ev_in[slot])
+            ids, fin = self.retrieve_reranked(reranker, qd[slot], K, q_rec, topk=topk, algo=algo)
+            ev_cmp[slot].record(s_cmp)
+            s_out.wait_event(ev_cmp[slot])
+            if to_host:
+                if hout[slot] is None or hout[slot][0].shape != ids.shape:
+                    hout[slot] = (torch.empty(ids.shape, dtype=ids.dtype).pin_memory(),
+                                  torch.empty(fin.shape, dtype=fin.dtype).pin_memory())
+                with torch.cuda.stream(s_out):
+                    hout[slot][0].copy_(ids, non_blocking=True)
+                    hout[slot][1].copy_(fin, non_blocking=True)
+                for t in (ids, fin):
+                    try:
+                        t.record_stream(s_out)
+                    except Exception:
+                        pass                            # views of the exchange region are not allocator-owned
+                res = hout[slot]
+            else:
+                res = (ids, fin)
+            ev_out[slot].record(s_out)
+            if pending is not None:
+                ev_out[pending[0]].synchronize()        # at most one batch in flight behind the caller
+                yield pending[1]
+            pending = (slot, res)
+        if pending is not None:
+            ev_out[pending[0]].synchronize()
+            yield pending[1]
+
     def _peer_exchange(self, b: int, K: int, queries):
         """The NVLink peer-memory exchange for (b, K), created on first use (collective: every rank
         calls with the same sizes).  ``use_peer=False`` or MMR_B200_NO_PEER=1 selects the NCCL path;

@@ -48,6 +48,14 @@ def _worker(rank, world, port, out_dir):
     assert torch.equal(rows2, rows) and torch.equal(scores2, scores)
     assert torch.equal(order2, order) and torch.equal(sc2, sc)
     assert torch.equal(ids4, want_ids) and torch.equal(fin4, want_fin)
+    # serving loop (pipelined copies) == direct calls, on every rank
+    batches = [torch.from_numpy(osr.to_bf16_round(synth.make_embeddings(b, d, seed=60 + i))).pin_memory() for i in range(4)]
+    got = [(i_.clone(), f_.clone()) for i_, f_ in s.serve(rer, iter(batches), k, q_rec, topk=20)]
+    assert len(got) == len(batches)
+    for hb, (g_ids, g_fin) in zip(batches, got):
+        w_ids, w_fin = s_nccl.retrieve_reranked(rer, hb.cuda(), k, q_rec, topk=20)
+        torch.cuda.synchronize()
+        assert torch.equal(g_ids, w_ids.cpu()) and torch.equal(g_fin, w_fin.cpu())
     for bb, kk in ((33, 50), (1, 10), (70, 64)):
         a_ids, a_fin = s.retrieve_reranked(rer, qd[:bb].contiguous(), kk, q_rec[:bb].contiguous(), topk=0)
         b_ids, b_fin = s_nccl.retrieve_reranked(rer, qd[:bb].contiguous(), kk, q_rec[:bb].contiguous(), topk=0)
@@ -77,3 +85,27 @@ def test_two_gpu_sharded_equals_single(tmp_path):
         z = np.load(tmp_path / f"r{rank}.npz")
         assert np.array_equal(z["rows"], single["rows"]) and np.array_equal(z["scores"], single["scores"])
         assert np.array_equal(z["order"], single["order"]) and np.allclose(z["sc"], single["sc"], rtol=0, atol=1e-12)
+
+
+def test_serve_loop_single_gpu():
+    """ShardedSearcher.serve on one GPU (no process group): pinned host batches in, host results out,
+    equal to the direct device call for every batch."""
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, synth
+    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher
+    from oracle import search as osr
+    n, d, b, k = 20000, 128, 300, 40
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=15))
+    rng = np.random.default_rng(17)
+    masks = rng.integers(0, 2 ** 43, size=n + b, dtype=np.uint64) & rng.integers(0, 2 ** 43, size=n + b, dtype=np.uint64)
+    kg = rng.standard_normal((n + b, 32)).astype(np.float32)
+    eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
+    rer = Reranker.from_tables(masks, kg, device=0)
+    s = ShardedSearcher(eng)
+    q_rec = torch.arange(n, n + b, device="cuda")
+    batches = [torch.from_numpy(osr.to_bf16_round(synth.make_embeddings(b, d, seed=30 + i))).pin_memory() for i in range(5)]
+    got = [(i_.clone(), f_.clone()) for i_, f_ in s.serve(rer, iter(batches), k, q_rec, topk=10)]
+    assert len(got) == 5
+    for hb, (g_ids, g_fin) in zip(batches, got):
+        w_ids, w_fin = s.retrieve_reranked(rer, hb.cuda(), k, q_rec, topk=10)
+        torch.cuda.synchronize()
+        assert g_ids.shape == (b, 10) and torch.equal(g_ids, w_ids.cpu()) and torch.equal(g_fin, w_fin.cpu())
