@@ -8,10 +8,13 @@ mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $out/gpu_$tag.txt
 python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1; echo "pytest exit=$?" >> $out/pytest_$tag.log
 tail -3 $out/pytest_$tag.log
+python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; echo "smoke exit=$?"
 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench exit=$?"
 cat $out/bench_$tag.json
 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json 2>> $out/bench_$tag.err
 cat $out/bench_ref_$tag.json
+python scripts/eval_cfg5.py > $out/cfg5_$tag.json 2>$out/cfg5_$tag.err; cat $out/cfg5_$tag.json
+python bench.py --rows 1000000 --batch 1024 --no-cpu-baseline --latency-queries 0 > $out/bench_cfg2_$tag.json 2>>$out/bench_$tag.err; cat $out/bench_cfg2_$tag.json
 small="--steps 2 --warmup 3 --no-cpu-baseline --latency-queries 3"
 python bench.py $small > $out/plain_$tag.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_$tag.csv \

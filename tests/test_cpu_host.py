@@ -86,3 +86,38 @@ def test_shard_bounds_cover_rows():
         b = [shard_bounds(n, w, r) for r in range(w)]
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def test_create_dump_embedding_matches_reference(tmp_path):
+    """createDumpEmbedding writes the reference's merged files (Helpers/dumpEmbedding.py:28-39); when the
+    reference is mounted its own function is run on a copy of the inputs and the outputs compared."""
+    import json
+    from multi_modal_retrieval_predict_project_b200.Helpers import createDumpEmbedding
+    rng = np.random.default_rng(5)
+    d = tmp_path / "embeddings"
+    d.mkdir()
+    tr, va = rng.standard_normal((7, 16)).astype(np.float32), rng.standard_normal((3, 16)).astype(np.float32)
+    np.save(d / "train_joint_embeddings.npy", tr)
+    np.save(d / "val_joint_embeddings.npy", va)
+    json.dump([f"t{i}" for i in range(7)], open(d / "train_ids.json", "w"))
+    json.dump([f"v{i}" for i in range(3)], open(d / "val_ids.json", "w"))
+    createDumpEmbedding(tmp_path, d)
+    merged = np.load(d / "trainval_joint_embeddings.npy")
+    assert merged.dtype == np.float32 and np.array_equal(merged, np.concatenate([tr, va]))
+    assert json.load(open(d / "trainval_ids.json")) == [f"t{i}" for i in range(7)] + [f"v{i}" for i in range(3)]
+    ref_file = "/root/reference/src/Helpers/dumpEmbedding.py"
+    if os.path.exists(ref_file):
+        import importlib.util
+        import sys
+        sys.dont_write_bytecode = True
+        spec = importlib.util.spec_from_file_location("_ref_dump_embedding", ref_file)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        d2 = tmp_path / "ref_embeddings"
+        d2.mkdir()
+        for f in ("train_joint_embeddings.npy", "val_joint_embeddings.npy", "train_ids.json", "val_ids.json"):
+            (d2 / f).write_bytes((d / f).read_bytes())
+        mod.EMBEDDINGS_DIR = d2          # the reference writes the ids next to its module-level default dir
+        mod.createDumpEmbedding(tmp_path, d2)
+        assert np.array_equal(np.load(d2 / "trainval_joint_embeddings.npy"), merged)
+        assert json.load(open(d2 / "trainval_ids.json")) == json.load(open(d / "trainval_ids.json"))

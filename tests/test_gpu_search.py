@@ -252,3 +252,22 @@ def test_gemm_large_k_generic_compaction():
         rows, scores = eng.search(q, k, algo="gemm")
         want_rows, want_scores = osr.exact_topk(q, g, k)
         _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+
+
+def test_merged_engine_from_split_dumps(tmp_path):
+    """Helpers.merged_engine: train + val dumps -> one HBM-resident gallery, rows and ids in the order
+    createDumpEmbedding writes them (reference Helpers/dumpEmbedding.py:28-39)."""
+    import json
+    from multi_modal_retrieval_predict_project_b200 import synth
+    from multi_modal_retrieval_predict_project_b200.Helpers import merged_engine
+    tr, va = synth.make_embeddings(300, 64, seed=111), synth.make_embeddings(120, 64, seed=112)
+    np.save(tmp_path / "train_joint_embeddings.npy", tr)
+    np.save(tmp_path / "val_joint_embeddings.npy", va)
+    json.dump([f"t{i}" for i in range(300)], open(tmp_path / "train_ids.json", "w"))
+    json.dump([f"v{i}" for i in range(120)], open(tmp_path / "val_ids.json", "w"))
+    eng = merged_engine(tmp_path, device=0)
+    assert eng.n == 420 and eng.ids[299] == "t299" and eng.ids[300] == "v0"
+    ids, scores = eng.retrieve(va[5], K=3)
+    assert ids[0] == "v5" and abs(scores[0] - 1.0) < 1e-5
+    want_rows, want_scores = osr.exact_topk(va[5:6], np.concatenate([tr, va]), 3)
+    assert ids == [eng.ids[int(r)] for r in want_rows[0]]
