@@ -579,6 +579,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int i = 0; i < kTrack; ++i) top[i] = (i < kTrack - pub_rank) ? INFINITY : -INFINITY;
     float published = -INFINITY;
     const bool track = tau_pub != nullptr && pub_rank <= kTrack && q_ok;
+    const bool probe = tau_pub != nullptr && pub_rank <= kTrack && (debug_flags & 2) == 0;  // warp-uniform
     const int epi_tid = threadIdx.x - (kFirstEpiWarp * 32 + group * kEpiThreads);  // 0..127
     const int64_t range_end = min(static_cast<int64_t>(tile_end) * kBlockN, n);
     const uint32_t full_bytes = static_cast<uint32_t>(cap - 32) * 8u;
@@ -631,6 +632,65 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         trace[static_cast<size_t>(blockIdx.x) * 64 + (t < 40 ? 1 + t : 40 + (t >> 5))] = now;
       }
 #endif
+      // ---- probe pass (first tile of this warpgroup only) -------------------------------------
+      // A list that starts with no threshold appends every score of its first two tiles (512 stores of
+      // 8 bytes scattered over 32 lists per instruction: ~60 us per tile, L2-write-bound) and then all 32
+      // lists of the warp are compacted (~175 us).  Instead the accumulator tile -- it stays in TMEM until
+      // this warpgroup releases the stage -- is read twice: the first pass only takes the 8 chunk maxima
+      // into the running top-8 and publishes the list's r-th best; after a short bounded wait for the
+      // other lists of the query (all parts run this step at the same time) the cross-list bound g prunes
+      // the REAL pass over the same tile and everything after it.  The maxima are not stored by the probe:
+      // the tracker is reset, the real pass re-appends them (they are >= this list's bound >= g), so the
+      // published claim "r entries >= bound in this list" holds from the end of the real pass on.
+      if (t == group && probe && (debug_flags & 1) == 0) {
+#pragma unroll 1
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          float m = -INFINITY;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float g0, g1, g2, g3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3)
+                         : "r"(ginv_s + static_cast<uint32_t>((c * 32 + j4 * 4) * 4)));
+            m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) * g0, __uint_as_float(v[j4 * 4 + 1]) * g1),
+                               fmaxf(__uint_as_float(v[j4 * 4 + 2]) * g2, __uint_as_float(v[j4 * 4 + 3]) * g3)));
+          }
+          float x = m * qinv;
+#pragma unroll
+          for (int i = 0; i < kTrack; ++i) {
+            const float hi = fmaxf(top[i], x);
+            x = fminf(top[i], x);
+            top[i] = hi;
+          }
+        }
+        if (track) {
+          const float rth = top[kTrack - 1];
+          if (rth > published) {
+            published = rth;
+            __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kTrack; ++i) top[i] = (i < kTrack - pub_rank) ? INFINITY : -INFINITY;
+        // bounded wait for the other lists of this query (lists of CTAs that are not resident yet never
+        // answer: after ~140 us the tile is processed without a bound, exactly as before; the host disables the
+        // probe when some list of the launch gets no tile at all)
+        for (int spin = 0; spin < 96; ++spin) {
+          uint32_t g = 0xFFFFFFFFu;
+          if (q_ok) {
+            for (int p = 0; p < n_lists; ++p) {
+              const uint32_t v = __ldcg(tau_pub + static_cast<int64_t>(p) * b_pad + q);
+              g = v < g ? v : g;
+            }
+            if (g != 0u) tau_pre = fmaxf(tau_pre, pre_threshold(ordered_to_f32(g), qinv));
+          }
+          if (__all_sync(0xffffffffu, !q_ok || g != 0u)) break;
+          __nanosleep(500);
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < ((debug_flags & 1) ? 0 : kBlockN / 32); ++c) {
         uint32_t v[32];
@@ -715,18 +775,46 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mbar_arrive_n(&aux->tmem_empty[group], 1);
       }
     }
-    // final exact top-k per list so that select.cu merges short lists
+    // final pass per list so that select.cu merges lists of <= k entries: first drop everything below the
+    // cross-list bound (one sweep, no selection; typically leaves 10-30 entries), and only if more than k
+    // remain select the exact top-k
     {
       int cnt = static_cast<int>(ptr - buf);
+      uint32_t gfin = 0u;  // ordered score; 0 = no bound
+      if (tau_pub != nullptr && q_ok && cnt > k) {
+        gfin = 0xFFFFFFFFu;
+        for (int p = 0; p < n_lists; ++p) {
+          const uint32_t v = __ldcg(tau_pub + static_cast<int64_t>(p) * b_pad + q);
+          gfin = v < gfin ? v : gfin;
+        }
+      }
       uint32_t need = __ballot_sync(0xffffffffu, q_ok && cnt > k);
       while (need != 0u) {
         const int src = __ffs(need) - 1;
         need &= need - 1u;
         uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
-        const int scnt = __shfl_sync(0xffffffffu, cnt, src);
+        int scnt = __shfl_sync(0xffffffffu, cnt, src);
+        const uint32_t gsrc = __shfl_sync(0xffffffffu, gfin, src);
         __syncwarp();
-        (void)warp_compact_dispatch(sbuf, scnt, k, k, cap, lane, nullptr);
-        if (lane == src) cnt = k;
+        if (gsrc != 0u) {  // stable in-place filter: kept entries only move to lower indices
+          int base = 0;
+          for (int i0 = 0; i0 < scnt; i0 += 32) {
+            const int i = i0 + lane;
+            const uint2 e = (i < scnt) ? sbuf[i] : make_uint2(0u, 0u);
+            const bool keep = i < scnt && f32_to_ordered(__uint_as_float(e.x)) >= gsrc;
+            const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) sbuf[base + __popc(mk & ((1u << lane) - 1u))] = e;
+            base += __popc(mk);
+            __syncwarp();
+          }
+          scnt = base;
+        }
+        if (scnt > k) {
+          (void)warp_compact_dispatch(sbuf, scnt, k, k, cap, lane, nullptr);
+          scnt = k;
+        }
+        if (lane == src) cnt = scnt;
       }
       if (q_ok) counts[static_cast<int64_t>(q) * n_lists + list] = cnt;
     }
@@ -863,6 +951,13 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).  MMR_B200_EARLY_TILES overrides.
   static const int early_env = std::getenv("MMR_B200_EARLY_TILES") ? std::atoi(std::getenv("MMR_B200_EARLY_TILES")) : -1;
   const int early_tiles = early_env >= 0 ? early_env : (plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0);
+  // probe pass (bit 1 of the flags disables it): only when every list of the launch gets at least one tile,
+  // i.e. every part -- the last one included -- has at least kEpiGroups tiles
+  int flags = debug_flags;
+  {
+    const int last_tiles = tiles_total - (plan.n_parts - 1) * plan.tiles_per_part;
+    if (plan.tiles_per_part < kEpiGroups || last_tiles < kEpiGroups) flags |= 2;
+  }
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
   MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));
@@ -890,7 +985,7 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
 #endif
   MMR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap, plan.m_tiles,
                                   plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total, sp.num_stages, pub_rank,
-                                  refresh, early_tiles, debug_flags, cand2, counts, tau_pub, trace));
+                                  refresh, early_tiles, flags, cand2, counts, tau_pub, trace));
   MMR_LAUNCHED();
 #ifdef MMR_GEMM_TRACE
   if (trace != nullptr) {

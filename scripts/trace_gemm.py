@@ -27,7 +27,7 @@ for name, sel in (("wave 1", ~wave2), ("wave 2", wave2)):
     if len(tt) == 0:
         continue
     print(name, "CTAs:", len(tt))
-    cols = [c for c in range(1, 64) if (tt[:, c] > 0).all()]
+    cols = [c for c in range(1, 64) if (tt[:, c] > 0).all() and (c <= 12 or c > 40)]
     for c in cols:
         us = (tt[:, c].astype(np.int64) - int(t0)) / 1e3
         print(f"  tile {(c - 1) if c <= 40 else 32 * (c - 40):5d}: min {us.min():9.1f}  med {np.median(us):9.1f}  max {us.max():9.1f}  spread {us.max() - us.min():7.1f} us")
