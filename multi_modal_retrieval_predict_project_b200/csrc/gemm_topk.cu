@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                  const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
                  int k, int cap, int m_tiles, int m_group, int n_parts, int tiles_per_part, int tiles_total,
-                 int num_stages,
+                 int num_stages, int pace_w,
                  int pub_rank, int refresh_tiles, int early_tiles, int debug_flags, uint2* __restrict__ cand,
                  int32_t* __restrict__ counts, uint32_t* __restrict__ tau_pub, unsigned long long* __restrict__ trace) {
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; the declaration requests it and the
@@ -480,9 +480,40 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                           m_tile * kBlockM);
           }
         }
+        // Pacing.  The units that stream the same gallery part share it through L2 only while they
+        // stay within a few tens of tiles of each other (126 MB of L2 / n_parts); once they drift apart
+        // every unit pulls its own copy from HBM and the ring (2 us of work) no longer hides the latency
+        // (measured: DRAM reads x2-3, -6 % at 10M rows).  Every 8 tiles the leader publishes its tile
+        // index and holds its loads while the slowest sharer of its part is more than pace_w tiles
+        // behind.  Advisory only: a sharer that makes no progress for ~100 us (not resident yet) switches
+        // pacing off for this unit; finished units publish "done".
+        uint32_t* const progress = (tau_pub != nullptr && pace_w > 0 && leader)
+                                       ? tau_pub + static_cast<size_t>(m_tiles) * kBlockM * (n_parts * kEpiGroups)
+                                       : nullptr;
+        const int n_share = min(m_group, m_units - (unit / per_group) * m_group);
+        volatile uint32_t* const shared_prog = progress != nullptr ? progress + (unit - rem) + part * m_group : nullptr;
+        bool pace_live = progress != nullptr && n_share > 1;
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < num_tiles; ++t) {
+          if (pace_live && (t & 7) == 0) {
+            *reinterpret_cast<volatile uint32_t*>(progress + unit) = static_cast<uint32_t>(t) + 1u;
+            if (t >= pace_w) {
+              for (int spins = 0;; ++spins) {
+                uint32_t slowest = 0xFFFFFFFFu;
+                for (int j = 0; j < n_share; ++j) {
+                  const uint32_t v = shared_prog[j];
+                  slowest = v < slowest ? v : slowest;
+                }
+                if (slowest + static_cast<uint32_t>(pace_w) >= static_cast<uint32_t>(t) + 1u) break;
+                if (spins > 256) {
+                  pace_live = false;
+                  break;
+                }
+                __nanosleep(256);
+              }
+            }
+          }
           // pair mode: this CTA stages gallery rows [n0, n0 + 128) of the pair's 256-row tile
           const int n0 = (tile_begin + t) * kBlockN + (kPair ? static_cast<int>(cta_rank) * (kBlockN / 2) : 0);
           for (int kc = 0; kc < num_kc; ++kc) {
@@ -509,6 +540,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           }
         }
+        if (progress != nullptr) *reinterpret_cast<volatile uint32_t*>(progress + unit) = 0xFFFFFFFFu;  // done
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
@@ -920,7 +952,12 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
   plan->cap = cap;
   plan->cand_bytes = static_cast<size_t>(b) * plan->n_lists * cap * sizeof(uint2);
   plan->count_bytes = static_cast<size_t>(b) * plan->n_lists * sizeof(int32_t);
-  plan->pub_bytes = static_cast<size_t>(m_tiles) * kBlockM * plan->n_lists * sizeof(uint32_t);
+  // published pruning bounds [n_lists][m_tiles * 128] followed by one pacing counter per scheduling unit
+  {
+    const int64_t groups = (m_units + plan->m_group - 1) / plan->m_group;
+    plan->pub_bytes = (static_cast<size_t>(m_tiles) * kBlockM * plan->n_lists +
+                       static_cast<size_t>(groups) * plan->m_group * plan->n_parts) * sizeof(uint32_t);
+  }
   return MMR_OK;
 }
 
@@ -950,6 +987,8 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   // 1M x 2048/4096 (16 sharers): without the synchronous first compaction the sharers drift apart
   // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).  MMR_B200_EARLY_TILES overrides.
   static const int early_env = std::getenv("MMR_B200_EARLY_TILES") ? std::atoi(std::getenv("MMR_B200_EARLY_TILES")) : -1;
+  static const int pace_env = std::getenv("MMR_B200_GEMM_PACE") ? std::atoi(std::getenv("MMR_B200_GEMM_PACE")) : -1;
+  const int pace_w = pace_env >= 0 ? pace_env : 64;
   const int early_tiles = early_env >= 0 ? early_env : (plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0);
   // probe pass (bit 1 of the flags disables it): only when every list of the launch gets at least one tile,
   // i.e. every part -- the last one included -- has at least kEpiGroups tiles
@@ -984,7 +1023,7 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   }
 #endif
   MMR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_g, inv_norm, q_inv, n, b, d_pad, k, plan.cap, plan.m_tiles,
-                                  plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total, sp.num_stages, pub_rank,
+                                  plan.m_group, plan.n_parts, plan.tiles_per_part, tiles_total, sp.num_stages, pace_w, pub_rank,
                                   refresh, early_tiles, flags, cand2, counts, tau_pub, trace));
   MMR_LAUNCHED();
 #ifdef MMR_GEMM_TRACE

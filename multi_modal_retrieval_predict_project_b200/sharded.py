@@ -63,19 +63,31 @@ class PeerExchange:
         self.world = dist.get_world_size(group)
         self.b_max, self.k_max = int(b_max), int(k_max)
         self.step = 0
+        # Every rank runs the same sequence of collectives whatever fails locally; ``self.error`` holds
+        # the local failure (None = mapped) and the caller agrees on the outcome across ranks.
+        self.error = None
+        self._h = None
         h = C.c_void_p()
+        mine = b""
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.mmr_exchange_create(C.byref(h), self.rank, self.world, self.b_max, self.k_max,
-                                                     self.device))
-            self._h = h
-            nbytes = self._lib.mmr_exchange_handle_bytes()
-            mine = C.create_string_buffer(nbytes)
-            _lib.check(self._lib.mmr_exchange_handle(self._h, mine))
+            try:
+                _lib.check(self._lib.mmr_exchange_create(C.byref(h), self.rank, self.world, self.b_max, self.k_max,
+                                                         self.device))
+                self._h = h
+                buf = C.create_string_buffer(self._lib.mmr_exchange_handle_bytes())
+                _lib.check(self._lib.mmr_exchange_handle(self._h, buf))
+                mine = bytes(buf.raw)
+            except Exception as e:  # noqa: BLE001
+                self.error = str(e)
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(mine.raw), group=group)
-            blob = b"".join(handles)
-            _lib.check(self._lib.mmr_exchange_open(self._h, blob))
-        dist.barrier(group=group)  # every rank has mapped every region before anybody stores into one
+            dist.all_gather_object(handles, mine, group=group)
+            if self.error is None and any(len(x) != len(mine) for x in handles):
+                self.error = "a peer rank could not create its exchange region"
+            if self.error is None:
+                try:
+                    _lib.check(self._lib.mmr_exchange_open(self._h, b"".join(handles)))
+                except Exception as e:  # noqa: BLE001
+                    self.error = str(e)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -329,10 +341,28 @@ class ShardedSearcher:
             return None
         px = getattr(self, "_px", None)
         if px is None or px.b_max < b or px.k_max < K:
+            import sys
+            import torch
+            import torch.distributed as dist
             if px is not None:
                 px.close()
-            self._px = px = PeerExchange(queries.device.index or 0, max(b, px.b_max if px else 0),
-                                         max(K, px.k_max if px else 0), group=self.group)
+            b_max, k_max = max(b, px.b_max if px else 0), max(K, px.k_max if px else 0)
+            # creating the regions and mapping the peers is collective; if ANY rank cannot map its peers
+            # (no P2P between the devices, IPC disabled) every rank falls back to the NCCL transport together
+            px = PeerExchange(queries.device.index or 0, b_max, k_max, group=self.group)
+            ok, err = (1, "") if px.error is None else (0, px.error)
+            flag = torch.tensor([ok], device=queries.device, dtype=torch.int32)
+            # (also the barrier: every rank has mapped every region before anybody stores into one)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:
+                if px is not None:
+                    px.close()
+                print(f"[mmr_b200] NVLink peer exchange unavailable ({err or 'a peer rank failed'}); "
+                      "using the NCCL all-gather transport", file=sys.stderr)
+                self.use_peer = False
+                self._px = None
+                return None
+            self._px = px
         return px
 
     def rerank(self, reranker, q_embs, rows, q_rec, cand_rec, topk: int = 0):
