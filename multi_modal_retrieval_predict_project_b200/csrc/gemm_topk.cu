@@ -987,15 +987,23 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   // 1M x 2048/4096 (16 sharers): without the synchronous first compaction the sharers drift apart
   // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).  MMR_B200_EARLY_TILES overrides.
   static const int early_env = std::getenv("MMR_B200_EARLY_TILES") ? std::atoi(std::getenv("MMR_B200_EARLY_TILES")) : -1;
+  // Short launches (<= 2048 tiles per part: the shards at N >= 4, cfg2, cfg5) run the probe pass + pacing:
+  // the ~300 us per-wave warm-up it removes is 10-25 % of such a launch.  Long launches keep the original
+  // start-up: its lockstep compactions keep the sharers of a gallery part aligned for the whole launch
+  // (ncu at 10M x 4096: L2 hit 78 % / 28.8 GB of DRAM reads, vs 68 % / 36.2 GB with probe + pacing, 2-5 % slower)
+  // and the warm-up is < 2 % there.  MMR_B200_GEMM_PROBE_MAX_TILES / MMR_B200_GEMM_PACE override.
+  static const int probe_max_env =
+      std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES") ? std::atoi(std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES")) : 2048;
+  const bool short_launch = plan.tiles_per_part <= probe_max_env;
   static const int pace_env = std::getenv("MMR_B200_GEMM_PACE") ? std::atoi(std::getenv("MMR_B200_GEMM_PACE")) : -1;
-  const int pace_w = pace_env >= 0 ? pace_env : 64;
+  const int pace_w = pace_env >= 0 ? pace_env : (short_launch ? 64 : 0);
   const int early_tiles = early_env >= 0 ? early_env : (plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0);
   // probe pass (bit 1 of the flags disables it): only when every list of the launch gets at least one tile,
   // i.e. every part -- the last one included -- has at least kEpiGroups tiles
   int flags = debug_flags;
   {
     const int last_tiles = tiles_total - (plan.n_parts - 1) * plan.tiles_per_part;
-    if (plan.tiles_per_part < kEpiGroups || last_tiles < kEpiGroups) flags |= 2;
+    if (plan.tiles_per_part < kEpiGroups || last_tiles < kEpiGroups || !short_launch) flags |= 2;
   }
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
