@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmr_b200.so")
+LIB_PATH = os.environ.get("MMR_B200_LIB") or os.path.join(_HERE, "libmmr_b200.so")  # override: A/B builds
 
 MMR_OK, MMR_EINVAL, MMR_ECUDA, MMR_ENOMEM, MMR_ENODEV, MMR_EUNSUP = range(6)
 MMR_F32, MMR_BF16 = 0, 1

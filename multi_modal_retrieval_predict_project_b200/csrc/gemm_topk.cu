@@ -386,7 +386,10 @@ __device__ __forceinline__ float pre_threshold(float tau, float qinv) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kResident, bool kPair>
+// kProbe: the short-launch variant (probe pass on the first tile, pacing of the sharers, bound-filtered
+// final pass).  It is a compile-time switch because the long-launch code must stay exactly as it was: the
+// same source with the extra paths merely disabled at run time measured 4-7 % slower at 10M x 4096.
+template <bool kResident, bool kPair, bool kProbe>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                  const float* __restrict__ inv_norm, const float* __restrict__ q_inv, int64_t n, int b, int d_pad,
@@ -487,7 +490,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // index and holds its loads while the slowest sharer of its part is more than pace_w tiles
         // behind.  Advisory only: a sharer that makes no progress for ~100 us (not resident yet) switches
         // pacing off for this unit; finished units publish "done".
-        uint32_t* const progress = (tau_pub != nullptr && pace_w > 0 && leader)
+        uint32_t* const progress = (kProbe && tau_pub != nullptr && pace_w > 0 && leader)
                                        ? tau_pub + static_cast<size_t>(m_tiles) * kBlockM * (n_parts * kEpiGroups)
                                        : nullptr;
         const int n_share = min(m_group, m_units - (unit / per_group) * m_group);
@@ -496,7 +499,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < num_tiles; ++t) {
-          if (pace_live && (t & 7) == 0) {
+          if (kProbe && pace_live && (t & 7) == 0) {
             *reinterpret_cast<volatile uint32_t*>(progress + unit) = static_cast<uint32_t>(t) + 1u;
             if (t >= pace_w) {
               for (int spins = 0;; ++spins) {
@@ -540,7 +543,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           }
         }
-        if (progress != nullptr) *reinterpret_cast<volatile uint32_t*>(progress + unit) = 0xFFFFFFFFu;  // done
+        if (kProbe && progress != nullptr) *reinterpret_cast<volatile uint32_t*>(progress + unit) = 0xFFFFFFFFu;  // done
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
@@ -611,7 +614,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int i = 0; i < kTrack; ++i) top[i] = (i < kTrack - pub_rank) ? INFINITY : -INFINITY;
     float published = -INFINITY;
     const bool track = tau_pub != nullptr && pub_rank <= kTrack && q_ok;
-    const bool probe = tau_pub != nullptr && pub_rank <= kTrack && (debug_flags & 2) == 0;  // warp-uniform
+    const bool probe = kProbe && tau_pub != nullptr && pub_rank <= kTrack && (debug_flags & 2) == 0;  // warp-uniform
     const int epi_tid = threadIdx.x - (kFirstEpiWarp * 32 + group * kEpiThreads);  // 0..127
     const int64_t range_end = min(static_cast<int64_t>(tile_end) * kBlockN, n);
     const uint32_t full_bytes = static_cast<uint32_t>(cap - 32) * 8u;
@@ -674,7 +677,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // the REAL pass over the same tile and everything after it.  The maxima are not stored by the probe:
       // the tracker is reset, the real pass re-appends them (they are >= this list's bound >= g), so the
       // published claim "r entries >= bound in this list" holds from the end of the real pass on.
-      if (t == group && probe && (debug_flags & 1) == 0) {
+      if (kProbe && t == group && probe && (debug_flags & 1) == 0) {
 #pragma unroll 1
         for (int c = 0; c < kBlockN / 32; ++c) {
           uint32_t v[32];
@@ -813,7 +816,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     {
       int cnt = static_cast<int>(ptr - buf);
       uint32_t gfin = 0u;  // ordered score; 0 = no bound
-      if (tau_pub != nullptr && q_ok && cnt > k) {
+      if (kProbe && tau_pub != nullptr && q_ok && cnt > k) {
         gfin = 0xFFFFFFFFu;
         for (int p = 0; p < n_lists; ++p) {
           const uint32_t v = __ldcg(tau_pub + static_cast<int64_t>(p) * b_pad + q);
@@ -828,7 +831,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int scnt = __shfl_sync(0xffffffffu, cnt, src);
         const uint32_t gsrc = __shfl_sync(0xffffffffu, gfin, src);
         __syncwarp();
-        if (gsrc != 0u) {  // stable in-place filter: kept entries only move to lower indices
+        if (kProbe && gsrc != 0u) {  // stable in-place filter: kept entries only move to lower indices
           int base = 0;
           for (int i0 = 0; i0 < scnt; i0 += 32) {
             const int i = i0 + lane;
@@ -973,8 +976,15 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   const int tiles_total = static_cast<int>((n + kBlockN - 1) / kBlockN);
   const int m_units = pair ? (plan.m_tiles + 1) / 2 : plan.m_tiles;
   const int grid = ((m_units + plan.m_group - 1) / plan.m_group) * plan.m_group * plan.n_parts * (pair ? 2 : 1);
-  auto kern = pair ? (sp.resident ? gemm_topk_kernel<true, true> : gemm_topk_kernel<false, true>)
-                   : (sp.resident ? gemm_topk_kernel<true, false> : gemm_topk_kernel<false, false>);
+  const int tiles_last = tiles_total - (plan.n_parts - 1) * plan.tiles_per_part;
+  static const int probe_max_env =
+      std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES") ? std::atoi(std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES")) : 2048;
+  // short launch, and every list of the launch gets at least one tile (else its bound is never published)
+  const bool probe = plan.tiles_per_part <= probe_max_env && plan.tiles_per_part >= kEpiGroups && tiles_last >= kEpiGroups;
+  auto kern = probe ? (pair ? (sp.resident ? gemm_topk_kernel<true, true, true> : gemm_topk_kernel<false, true, true>)
+                            : (sp.resident ? gemm_topk_kernel<true, false, true> : gemm_topk_kernel<false, false, true>))
+                    : (pair ? (sp.resident ? gemm_topk_kernel<true, true, false> : gemm_topk_kernel<false, true, false>)
+                            : (sp.resident ? gemm_topk_kernel<true, false, false> : gemm_topk_kernel<false, false, false>));
   MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sp.total)));
   // threshold exchange: rank published per part and refresh period (in gallery tiles)
   // MMR_B200_GEMM_DEBUG bit 0: skip the epilogue's score processing (results are garbage) to
@@ -987,24 +997,15 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   // 1M x 2048/4096 (16 sharers): without the synchronous first compaction the sharers drift apart
   // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).  MMR_B200_EARLY_TILES overrides.
   static const int early_env = std::getenv("MMR_B200_EARLY_TILES") ? std::atoi(std::getenv("MMR_B200_EARLY_TILES")) : -1;
-  // Short launches (<= 2048 tiles per part: the shards at N >= 4, cfg2, cfg5) run the probe pass + pacing:
+  // Short launches (<= 2048 tiles per part: the shards at N >= 4, cfg2, cfg5) run the kProbe kernel:
   // the ~300 us per-wave warm-up it removes is 10-25 % of such a launch.  Long launches keep the original
   // start-up: its lockstep compactions keep the sharers of a gallery part aligned for the whole launch
-  // (ncu at 10M x 4096: L2 hit 78 % / 28.8 GB of DRAM reads, vs 68 % / 36.2 GB with probe + pacing, 2-5 % slower)
+  // (ncu at 10M x 4096: L2 hit 78 % / 28.8 GB of DRAM reads, vs 68 % / 36.2 GB with probe + pacing)
   // and the warm-up is < 2 % there.  MMR_B200_GEMM_PROBE_MAX_TILES / MMR_B200_GEMM_PACE override.
-  static const int probe_max_env =
-      std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES") ? std::atoi(std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES")) : 2048;
-  const bool short_launch = plan.tiles_per_part <= probe_max_env;
   static const int pace_env = std::getenv("MMR_B200_GEMM_PACE") ? std::atoi(std::getenv("MMR_B200_GEMM_PACE")) : -1;
-  const int pace_w = pace_env >= 0 ? pace_env : (short_launch ? 64 : 0);
+  const int pace_w = pace_env >= 0 ? pace_env : 64;  // only read by the kProbe kernel
   const int early_tiles = early_env >= 0 ? early_env : (plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0);
-  // probe pass (bit 1 of the flags disables it): only when every list of the launch gets at least one tile,
-  // i.e. every part -- the last one included -- has at least kEpiGroups tiles
-  int flags = debug_flags;
-  {
-    const int last_tiles = tiles_total - (plan.n_parts - 1) * plan.tiles_per_part;
-    if (plan.tiles_per_part < kEpiGroups || last_tiles < kEpiGroups || !short_launch) flags |= 2;
-  }
+  const int flags = debug_flags;  // bit 0: skip the score processing, bit 1: no probe pass in the kProbe kernel
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
   MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));
