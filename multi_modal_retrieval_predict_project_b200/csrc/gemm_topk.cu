@@ -6,13 +6,17 @@
 //
 //   scores[m, n] = sum_d Q[m, d] * G[n, d]      Q: (b, d_pad) bf16, G: (n, d_pad) bf16, both K-major
 //
-// CTA = (query tile of 128 rows) x (contiguous range of gallery tiles of 256 rows), 12 warps:
-//   warp 0    TMA producer: cp.async.bulk.tensor, 128B-swizzled [256 x 64] gallery chunks into a stage
-//             ring (mbarrier complete_tx).  For d_pad <= 512 the [128 x d_pad] query tile is loaded once
-//             and stays resident in shared memory; otherwise query chunks stream with the gallery.
-//   warp 1    MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
-//             fp32 accumulators in TMEM (2 stages x 256 columns); tcgen05.commit frees smem stages and
-//             publishes finished accumulators.  Warps 2-3 idle (they donate registers).
+// Work unit = a CTA PAIR (2-CTA cluster, cta_group::2; a single CTA when the batch has one query tile):
+// 2 x 128 queries x a contiguous range of gallery tiles of 256 rows.  Per CTA, 12 warps:
+//   warp 0    TMA producer: cp.async.bulk.tensor, 128B-swizzled gallery chunks into a stage ring (mbarrier
+//             complete_tx).  In a pair each CTA stages only ITS half of the gallery tile ([128 x 64] chunks)
+//             and all bytes are credited to the leader CTA's barriers.  For d_pad <= 512 the CTA's
+//             [128 x d_pad] query tile is loaded once and stays resident in shared memory; otherwise query
+//             chunks stream with the gallery.
+//   warp 1    MMA issuer (leader CTA only in a pair): one lane issues tcgen05.mma.kind::f16 (M=128 per CTA,
+//             256 per pair, N=256, K=16), fp32 accumulators in TMEM (2 stages x 256 columns);
+//             tcgen05.commit (multicast to both CTAs of a pair) frees smem stages and publishes finished
+//             accumulators.  Warps 2-3 idle (they donate registers).
 //   warps 4-11 epilogue, two warpgroups: group g owns accumulator stage g, i.e. gallery tiles g, g+2, ...
 //             so each group has two MMA tile times per tile.  thread <-> query row (TMEM lane).
 //             tcgen05.ld 32 columns -> t = acc * inv_norm(g) -> chunk max; only if some lane's max beats
@@ -26,6 +30,9 @@
 // across lists, every list publishes the score of its r-th best, r = ceil(k / n_lists): if every
 // list holds >= r candidates >= g = min over lists, the union holds >= k, so nothing below g can be
 // in the global top-k and all CTAs of the query tile prune with g.  select.cu merges the lists.
+// Short launches run the kProbe instantiation: a probe pass over the first tile seeds g before anything is
+// appended, the leaders pace themselves on the slowest sharer of their gallery part, and the final per-list
+// pass filters by g before any exact selection (see the comments at those sites and DESIGN.md section 4).
 //
 // Roofline: tensor-core bound, 2 * b * n * d_pad FLOP per launch.
 #include <cuda.h>
