@@ -121,3 +121,45 @@ def test_create_dump_embedding_matches_reference(tmp_path):
         mod.createDumpEmbedding(tmp_path, d2)
         assert np.array_equal(np.load(d2 / "trainval_joint_embeddings.npy"), merged)
         assert json.load(open(d2 / "trainval_ids.json")) == json.load(open(d / "trainval_ids.json"))
+
+
+def test_label_attention_pooling_matches_reference_module(tmp_path):
+    """Reranker._pool with a LabelAttention checkpoint (Linear -> Tanh -> Linear -> softmax ->
+    weighted sum, reference KnowledgeGraph/label_attention.py:11-27) and the mean-pool fallback
+    (Retrieval/reranker.py:84-86,219-220).  The torch module is the reference's own class when
+    /root/reference is mounted, an identical restatement otherwise."""
+    import torch
+    import torch.nn as nn
+    from multi_modal_retrieval_predict_project_b200.Retrieval.reranker import Reranker
+    ref_file = "/root/reference/src/KnowledgeGraph/label_attention.py"
+    if os.path.exists(ref_file):
+        import importlib.util
+        import sys
+        sys.dont_write_bytecode = True
+        spec = importlib.util.spec_from_file_location("_ref_label_attention", ref_file)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        LabelAttention = mod.LabelAttention
+    else:
+        class LabelAttention(nn.Module):
+            def __init__(self, d_emb, hidden=64):
+                super().__init__()
+                self.attn = nn.Sequential(nn.Linear(d_emb, hidden), nn.Tanh(), nn.Linear(hidden, 1))
+
+            def forward(self, label_embs, mask=None):
+                w = torch.softmax(self.attn(label_embs).squeeze(-1), dim=1)
+                return torch.bmm(w.unsqueeze(1), label_embs).squeeze(1), w
+    torch.manual_seed(3)
+    d, hidden = 24, 16
+    model = LabelAttention(d, hidden).eval()
+    ckpt = tmp_path / "label_attention_model.pt"
+    torch.save({"model_state": model.state_dict()}, ckpt)
+    rr = object.__new__(Reranker)                       # host-side pooling only: no tables, no GPU
+    rr.attn_params = Reranker._load_label_attention(ckpt, hidden)
+    x = torch.randn(5, d)
+    with torch.no_grad():
+        want, _ = model(x.unsqueeze(0))
+    got = rr._pool(x.numpy())
+    assert got.shape == (d,) and np.allclose(got, want.squeeze(0).numpy(), rtol=1e-5, atol=1e-6)
+    rr.attn_params = Reranker._load_label_attention(tmp_path / "missing.pt", hidden)
+    assert rr.attn_params is None and np.allclose(rr._pool(x.numpy()), x.numpy().mean(axis=0))
