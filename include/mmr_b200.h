@@ -253,6 +253,16 @@ int mmr_first_relevant_rank(mmr_index* index, const void* q, int32_t b, int32_t 
                             const uint64_t* g_masks, int32_t label_words, int64_t* out_rank,
                             int64_t* out_total, void* stream);
 
+/* evaluate_label_attention's retrieval metrics (Trainner/train_label_attention.py:106-125) over n record
+ * embeddings (n, d) fp32 with their L2 norms (np.linalg.norm, :108) and label bit masks: per record i,
+ * over the full ranking of all n items by cosine dot / (norm_i * norm_j) (self included with label 0;
+ * relevant = labels share a positive), out[i][0] = sklearn average_precision_score and out[i][1 + t] =
+ * mean relevance of the top topk[t] items ("recall@k" in the reference).  n_topk <= 8.  The caller
+ * averages over i (np.mean, :123-124). */
+int mmr_label_ranking_eval(const float* emb, const float* norms, int32_t n, int32_t d, const uint64_t* label_masks,
+                           int32_t label_words, const int32_t* topk, int32_t n_topk, double* out, int32_t device,
+                           void* stream);
+
 /* Result-set diversity (Evaluate/retrieval_diversity_compute.py:171-194): emb (b, k, d) fp32 ->
  * 1 - mean pairwise cosine (compute_embedding_diversity; 0 for fewer than 2 items) and label masks
  * (b, k, label_words) -> |union of labels| / mean label count over the items that have labels

@@ -136,3 +136,28 @@ def compute_label_diversity_from_labels(labels_list, device=None) -> float:
             m[0, i, idx[l] // 64] |= np.uint64(1) << np.uint64(idx[l] % 64)
     _, ol = result_diversity_batch(None, m, None, device)
     return float(ol[0])
+
+
+def evaluate_label_ranking(embs, label_vals, topk=(1, 5, 10), device=None, return_table: bool = False):
+    """Retrieval metrics of ``evaluate_label_attention`` (reference
+    ``Trainner/train_label_attention.py:106-125``) for record embeddings ``(n, d)`` and their multi-hot
+    labels ``(n, L)``: ``{"recall@k": ..., "mAP": ...}`` -- all-pairs cosine, full ranking per record
+    (self kept with label 0), mean relevance of the top k and sklearn's average precision, averaged over
+    the records.  One kernel (``mmr_label_ranking_eval``): no (n, n) matrix, no argsort, no Python loop."""
+    import torch
+    e = np.ascontiguousarray(embs, dtype=np.float32)
+    n, d = e.shape
+    norms = np.ascontiguousarray(np.linalg.norm(e, axis=1), dtype=np.float32)      # :108
+    masks = label_masks(np.asarray(label_vals).astype(int))
+    ks = np.ascontiguousarray(list(topk), dtype=np.int32)
+    if len(ks) > 8:
+        raise ValueError("at most 8 cut-offs")
+    out = np.zeros((n, 1 + len(ks)), dtype=np.float64)
+    dev = _lib.require_cuda(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mmr_label_ranking_eval(_lib.ptr(e), _lib.ptr(norms), n, d, _lib.ptr(masks), masks.shape[1],
+                                              _lib.ptr(ks), len(ks), _lib.ptr(out), dev, _lib.current_stream(dev)))
+    results = {f"recall@{int(k)}": float(np.mean(out[:, 1 + t])) for t, k in enumerate(ks)}
+    results["mAP"] = float(np.mean(out[:, 0]))
+    return (results, out) if return_table else results

@@ -62,6 +62,7 @@ SIGNATURES = {
     "mmr_rerank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f64, _f64, _f64, _i32, _vp, _vp, _vp],
     "mmr_metrics": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "mmr_first_relevant_rank": [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
+    "mmr_label_ranking_eval": [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp],
     "mmr_result_diversity": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "mmr_label_relevance": [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, _vp],
 }

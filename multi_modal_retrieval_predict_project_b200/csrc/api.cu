@@ -855,6 +855,28 @@ int mmr_first_relevant_rank(mmr_index* ix, const void* q, int32_t b, int32_t q_d
   return cs.finish();
 }
 
+int mmr_label_ranking_eval(const float* emb, const float* norms, int32_t n, int32_t d, const uint64_t* label_masks,
+                           int32_t label_words, const int32_t* topk, int32_t n_topk, double* out, int32_t device,
+                           void* stream_v) {
+  MMR_REQUIRE(n >= 0 && d >= 1 && label_words >= 1 && n_topk >= 0 && n_topk <= 8, "mmr_label_ranking_eval: bad sizes");
+  if (n == 0) return MMR_OK;
+  MMR_REQUIRE(emb && norms && label_masks && out && (topk || n_topk == 0), "mmr_label_ranking_eval: NULL argument");
+  MMR_TRY(check_device(device, nullptr));
+  DeviceGuard guard(device);
+  CallScope cs(static_cast<cudaStream_t>(stream_v));
+  const float *d_e, *d_n;
+  const uint64_t* d_m;
+  const int32_t* d_k;
+  double* d_out;
+  MMR_TRY(cs.in(emb, static_cast<size_t>(n) * d, &d_e));
+  MMR_TRY(cs.in(norms, static_cast<size_t>(n), &d_n));
+  MMR_TRY(cs.in(label_masks, static_cast<size_t>(n) * label_words, &d_m));
+  MMR_TRY(cs.in(topk, static_cast<size_t>(n_topk), &d_k));
+  MMR_TRY(cs.out(out, static_cast<size_t>(n) * (1 + n_topk), &d_out));
+  MMR_TRY(launch_label_ranking(d_e, d_n, n, d, d_m, label_words, d_k, n_topk, d_out, cs.stream));
+  return cs.finish();
+}
+
 int mmr_result_diversity(const float* emb, const uint64_t* label_masks, const int32_t* counts, int32_t b, int32_t k,
                          int32_t d, int32_t label_words, double* out_emb_div, double* out_label_div, int32_t device,
                          void* stream_v) {

@@ -157,7 +157,103 @@ diversity_kernel(const float* __restrict__ emb, const uint64_t* __restrict__ mas
   }
 }
 
+// label_ranking_kernel -- evaluate_label_attention (reference Trainner/train_label_attention.py:106-125):
+// all-pairs cosine of N record embeddings, and per query i over the FULL ranking of all N items
+// (self included, with label 0): mean of the relevance flags among the top-k ("recall@k" in the
+// reference's naming) and sklearn's average_precision_score.  No (N, N) matrix, no argsort: with
+//   tp(s) = #relevant with score >= s,  all(s) = #items with score >= s
+// average precision = (1/|rel|) * sum over relevant j of tp(s_j) / all(s_j)  (ties share one threshold,
+// exactly sklearn's step-wise definition), and item j is in the top-k iff fewer than k items are ranked
+// ahead of it (score desc, row asc).  One CTA per query; dynamic smem: n scores + n flags.
+__global__ void __launch_bounds__(256)
+label_ranking_kernel(const float* __restrict__ emb, const float* __restrict__ norms, int n, int d,
+                     const uint64_t* __restrict__ masks, int words, const int32_t* __restrict__ topk, int n_topk,
+                     double* __restrict__ out) {
+  extern __shared__ __align__(16) float sm_scores[];
+  uint8_t* const rel = reinterpret_cast<uint8_t*>(sm_scores + n);
+  __shared__ double s_ap[8];
+  __shared__ int s_hits[8][8];
+  __shared__ int s_nrel[8];
+  const int qi = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* q = emb + static_cast<int64_t>(qi) * d;
+  const float qn = norms[qi];
+  const uint64_t* qm = masks + static_cast<int64_t>(qi) * words;
+  // phase 1: sims[i][j] = dot / (norm_i * norm_j)  (:108-109), relevance = labels share a positive, self excluded (:114-115)
+  for (int j = warp; j < n; j += 8) {
+    const float* g = emb + static_cast<int64_t>(j) * d;
+    float acc = 0.f;
+    for (int t = lane; t < d; t += 32) acc = fmaf(g[t], q[t], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sm_scores[j] = acc / (qn * norms[j]);
+      uint64_t any = 0;
+      for (int w = 0; w < words; ++w) any |= qm[w] & masks[static_cast<int64_t>(j) * words + w];
+      rel[j] = (any != 0 && j != qi) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  // phase 2: every relevant item looks at the whole ranking
+  double ap = 0.0;
+  int hits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int nrel = 0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    if (rel[j] == 0) continue;
+    ++nrel;
+    const float sj = sm_scores[j];
+    int ge_all = 0, ge_rel = 0, ahead = 0;
+    for (int m = 0; m < n; ++m) {
+      const float s = sm_scores[m];
+      const bool ge = s >= sj;
+      ge_all += ge ? 1 : 0;
+      ge_rel += (ge && rel[m] != 0) ? 1 : 0;
+      ahead += (s > sj || (s == sj && m < j)) ? 1 : 0;
+    }
+    ap += static_cast<double>(ge_rel) / static_cast<double>(ge_all);
+    for (int t = 0; t < n_topk; ++t) hits[t] += ahead < topk[t] ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ap += __shfl_xor_sync(0xffffffffu, ap, o);
+    nrel += __shfl_xor_sync(0xffffffffu, nrel, o);
+    for (int t = 0; t < 8; ++t) hits[t] += __shfl_xor_sync(0xffffffffu, hits[t], o);
+  }
+  if (lane == 0) {
+    s_ap[warp] = ap;
+    s_nrel[warp] = nrel;
+    for (int t = 0; t < 8; ++t) s_hits[warp][t] = hits[t];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    int r = 0;
+    for (int w = 0; w < 8; ++w) {
+      a += s_ap[w];
+      r += s_nrel[w];
+    }
+    double* o = out + static_cast<int64_t>(qi) * (1 + n_topk);
+    o[0] = r == 0 ? 0.0 : a / static_cast<double>(r);  // sklearn: no positive => 0
+    for (int t = 0; t < n_topk; ++t) {
+      int h = 0;
+      for (int w = 0; w < 8; ++w) h += s_hits[w][t];
+      o[1 + t] = static_cast<double>(h) / static_cast<double>(topk[t]);  // sorted_labels[:k].mean()  (:121)
+    }
+  }
+}
+
 }  // namespace
+
+int launch_label_ranking(const float* emb, const float* norms, int n, int d, const uint64_t* masks, int words,
+                         const int32_t* topk, int n_topk, double* out, cudaStream_t stream) {
+  if (n == 0) return MMR_OK;
+  const size_t smem = static_cast<size_t>(n) * (sizeof(float) + 1) + 16;
+  if (smem > 200 * 1024) return fail(MMR_EUNSUP, "label ranking evaluation: more than ~40k records");
+  if (smem > 48 * 1024)
+    MMR_CUDA_TRY(cudaFuncSetAttribute(label_ranking_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  label_ranking_kernel<<<n, 256, smem, stream>>>(emb, norms, n, d, masks, words, topk, n_topk, out);
+  MMR_LAUNCHED();
+  return MMR_OK;
+}
 
 int launch_first_relevant_rank(const void* emb, int dtype_store, const float* inv_norm, int64_t n, int d_pad,
                                const float* q_f32, const float* q_inv, int b, const uint64_t* q_masks,

@@ -120,6 +120,8 @@ int launch_first_relevant_rank(const void* emb, int dtype_store, const float* in
                                const float* q_f32, const float* q_inv, int b, const uint64_t* q_masks,
                                const uint64_t* g_masks, int words, int64_t* out_rank, int64_t* out_total,
                                cudaStream_t stream);
+int launch_label_ranking(const float* emb, const float* norms, int n, int d, const uint64_t* masks, int words,
+                         const int32_t* topk, int n_topk, double* out, cudaStream_t stream);
 int launch_diversity(const float* emb, const uint64_t* masks, const int32_t* counts, int b, int k, int d, int words,
                      double* out_emb_div, double* out_label_div, cudaStream_t stream);
 

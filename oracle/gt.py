@@ -72,3 +72,48 @@ def compute_label_diversity_from_labels(labels_list) -> float:
     if not sizes:
         return 0.0
     return float(len(all_labels) / float(np.mean(sizes)))
+
+
+def average_precision_binary(labels, scores) -> float:
+    """sklearn.metrics.average_precision_score for binary labels (the call at reference
+    Trainner/train_label_attention.py:122), restated: thresholds at the distinct score values taken
+    in decreasing order, precision P_n = tp/(tp+fp) and recall R_n = tp/|positives| at each, AP =
+    sum_n (R_n - R_{n-1}) * P_n; 0.0 when there is no positive."""
+    labels = np.asarray(labels).astype(np.int64)
+    scores = np.asarray(scores)
+    npos = int(labels.sum())
+    if npos == 0:
+        return 0.0
+    order = np.argsort(-scores, kind="mergesort")
+    s, y = scores[order], labels[order]
+    last_of_threshold = np.r_[np.nonzero(np.diff(s))[0], len(s) - 1]
+    tps = np.cumsum(y)[last_of_threshold].astype(np.float64)
+    fps = (1 + last_of_threshold - tps).astype(np.float64)
+    precision = tps / (tps + fps)
+    recall = tps / npos
+    return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+
+
+def label_ranking_eval(embs: np.ndarray, label_vals: np.ndarray, topk=(1, 5, 10)):
+    """The retrieval metrics of evaluate_label_attention (reference
+    Trainner/train_label_attention.py:106-125) given the record embeddings: all-pairs cosine, per
+    record the relevance flags (labels share a positive, self = 0) in descending-similarity order,
+    ``recall@k`` = their mean over the first k, AP over the full ranking; means over the records.
+    Returns (results dict, per-record table (n, 1 + len(topk)) = [AP, recall@k...])."""
+    all_embs = np.asarray(embs)
+    norms = np.linalg.norm(all_embs, axis=1, keepdims=True)
+    sims = all_embs @ all_embs.T / (norms @ norms.T)                      # :108-109
+    vals = np.asarray(label_vals).astype(np.int64)
+    n = all_embs.shape[0]
+    table = np.zeros((n, 1 + len(topk)), dtype=np.float64)
+    for i in range(n):
+        labels = ((vals & vals[i]).sum(axis=1) > 0).astype(int)         # :114
+        labels[i] = 0                                                     # :115
+        idx = np.argsort(-sims[i])                                        # :118
+        sorted_labels = labels[idx]
+        table[i, 0] = average_precision_binary(labels, sims[i])           # :122
+        for t, k in enumerate(topk):
+            table[i, 1 + t] = sorted_labels[:k].mean()                    # :121
+    results = {f"recall@{k}": float(np.mean(table[:, 1 + t])) for t, k in enumerate(topk)}
+    results["mAP"] = float(np.mean(table[:, 0]))
+    return results, table

@@ -234,3 +234,26 @@ def test_compute_ranking_metrics_large_gallery_vs_oracle():
         got = compute_ranking_metrics(q, g, ql, gl, k=k)
         want = ogt.compute_ranking_metrics(q, g, ql, gl, k=k)
         assert np.isclose(got[0], want[0], rtol=1e-9) and got[1] == want[1] and np.isclose(got[2], want[2], rtol=1e-9)
+
+
+def test_label_ranking_eval_vs_oracle():
+    """Evaluate.evaluate_label_ranking (mmr_label_ranking_eval) == the restated evaluate_label_attention
+    metrics (reference Trainner/train_label_attention.py:106-125): AP over the full ranking and
+    mean relevance of the top k, per record and averaged."""
+    from multi_modal_retrieval_predict_project_b200.Evaluate import evaluate_label_ranking
+    from oracle import gt as ogt
+    rng = np.random.default_rng(21)
+    for n, d, L in ((300, 48, 14), (1000, 300, 43)):
+        # integer-valued embeddings with amp^2 * d < 2^24: every fp32 dot product is exact in any summation
+        # order, so the device and numpy/BLAS see bit-identical similarities (no near-tie reorderings)
+        amp = int(np.sqrt(2.0 ** 24 / d)) // 2
+        embs = rng.integers(-amp, amp + 1, size=(n, d)).astype(np.float32)
+        vals = (rng.random((n, L)) < 0.08).astype(int)
+        vals[3] = 0                                              # a record without labels: AP 0, recall 0
+        got, table = evaluate_label_ranking(embs, vals, topk=(1, 5, 10), device=0, return_table=True)
+        want, wtable = ogt.label_ranking_eval(embs, vals, topk=(1, 5, 10))
+        assert np.allclose(table, wtable, rtol=0, atol=1e-9), np.abs(table - wtable).max()
+        assert set(got) == set(want)
+        for key in want:
+            assert abs(got[key] - want[key]) < 1e-9, key
+        assert table[3, 0] == 0.0

@@ -157,3 +157,28 @@ def test_diversity_matches_reference():
         e = np.array(c["emb"], dtype=np.float32).reshape(len(c["emb"]), -1) if c["emb"] else np.zeros((0, 4), np.float32)
         assert np.isclose(ogt.compute_embedding_diversity(e), c["emb_div"], rtol=0, atol=1e-7)
         assert ogt.compute_label_diversity_from_labels(c["labels"]) == c["label_div"]
+
+
+def test_average_precision_restatement_matches_sklearn():
+    """oracle.gt.average_precision_binary == sklearn.metrics.average_precision_score (the function the
+    reference calls at Trainner/train_label_attention.py:122), incl. tied scores and the no-positive case;
+    label_ranking_eval's table is consistent with it."""
+    import warnings
+    from sklearn.metrics import average_precision_score
+    from oracle import gt as ogt
+    rng = np.random.default_rng(11)
+    for trial in range(30):
+        n = int(rng.integers(2, 60))
+        y = (rng.random(n) < 0.3).astype(int)
+        s = rng.standard_normal(n).astype(np.float32)
+        if trial % 3 == 0:
+            s = np.round(s, 1)                                   # many ties
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = float(average_precision_score(y, s)) if y.sum() > 0 else 0.0
+        assert abs(ogt.average_precision_binary(y, s) - want) < 1e-12, trial
+    embs = rng.standard_normal((40, 8)).astype(np.float32)
+    vals = (rng.random((40, 6)) < 0.2).astype(int)
+    res, table = ogt.label_ranking_eval(embs, vals, topk=(1, 5))
+    assert set(res) == {"recall@1", "recall@5", "mAP"} and table.shape == (40, 3)
+    assert abs(res["mAP"] - table[:, 0].mean()) < 1e-15 and np.all((table >= 0) & (table <= 1))
