@@ -353,6 +353,50 @@ class B200RetrievalEngine(RetrievalEngine):
                                                     _lib.current_stream(self.device)))
         return out
 
+    # -- "next" row f1: persisted device-format gallery ---------------------------------------------
+    def save_blob(self, path: str, chunk: int = 1 << 18) -> str:
+        """Write the gallery exactly as it is stored in HBM (bf16 indexes: the ROUNDED values as raw
+        bf16 bits -- half the bytes of the ``.npy`` the reference writes, and no fp32 -> bf16 pass on
+        reload) plus the ids, as one ``.npz``.  ``load_blob`` rebuilds a bit-identical index."""
+        import json
+        import torch
+        parts = []
+        for s in range(0, self.n, chunk):
+            rows = np.arange(s, min(self.n, s + chunk), dtype=np.int64) + self.row_offset
+            out = np.empty((len(rows), self.dim), dtype=np.float32)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.mmr_index_get_rows(self._handle, _lib.ptr(rows), len(rows), _lib.ptr(out),
+                                                        _lib.current_stream(self.device)))
+            if self.dtype == "bfloat16":
+                bits = out.view(np.uint32)
+                assert not np.any(bits & np.uint32(0xFFFF)), "stored values are not bf16-representable"
+                parts.append((bits >> np.uint32(16)).astype(np.uint16))
+            else:
+                parts.append(out)
+        data = np.concatenate(parts, axis=0) if parts else np.zeros((0, self.dim), np.float32)
+        ids = None if isinstance(self.ids, _VirtualIds) else json.dumps([str(i) for i in self.ids])
+        meta = json.dumps({"dtype": self.dtype, "n": self.n, "dim": self.dim, "row_offset": self.row_offset})
+        if not str(path).endswith(".npz"):
+            path = str(path) + ".npz"
+        np.savez(path, data=data, meta=np.array(meta), ids=np.array(ids if ids is not None else ""))
+        return str(path)
+
+    @classmethod
+    def load_blob(cls, path: str, **kwargs) -> "B200RetrievalEngine":
+        """Engine from a ``save_blob`` file: the stored values go to the device unchanged."""
+        import json
+        import torch
+        z = np.load(path, allow_pickle=False)
+        meta = json.loads(str(z["meta"]))
+        ids_json = str(z["ids"])
+        ids = json.loads(ids_json) if ids_json else None
+        kwargs.setdefault("row_offset", int(meta["row_offset"]))
+        kwargs.setdefault("keep_host", False)
+        if meta["dtype"] == "bfloat16":
+            t = torch.from_numpy(np.ascontiguousarray(z["data"]).view(np.int16)).view(torch.bfloat16)
+            return cls.from_arrays(t, ids=ids, dtype="bfloat16", **kwargs)
+        return cls.from_arrays(np.ascontiguousarray(z["data"], dtype=np.float32), ids=ids, dtype="float32", **kwargs)
+
     # -- "next" row: the link graph of the legacy engine, built on the GPU -------------------------
     def build_link_graph(self, threshold: float = 0.5, max_links: int = 10, batch: int = 4096) -> List[List[int]]:
         """``DLSRetrievalEngine._build_link_graph`` (reference ``retrieval.py:121-138``) as GPU

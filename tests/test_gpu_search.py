@@ -271,3 +271,28 @@ def test_merged_engine_from_split_dumps(tmp_path):
     assert ids[0] == "v5" and abs(scores[0] - 1.0) < 1e-5
     want_rows, want_scores = osr.exact_topk(va[5:6], np.concatenate([tr, va]), 3)
     assert ids == [eng.ids[int(r)] for r in want_rows[0]]
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float32"])
+def test_blob_round_trip_is_bit_identical(tmp_path, dtype):
+    """save_blob / load_blob (persisted device-format gallery): the reloaded index
+    returns bit-identical rows and scores; a bf16 blob holds the rounded values as raw bf16 bits."""
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, synth
+    g = synth.make_embeddings(3000, 100, seed=121)
+    q = synth.make_embeddings(37, 100, seed=122)
+    ids = [f"r{i}" for i in range(3000)]
+    eng = B200RetrievalEngine.from_arrays(g, ids=ids, dtype=dtype, device=0)
+    path = eng.save_blob(str(tmp_path / "gallery"))
+    eng2 = B200RetrievalEngine.load_blob(path, device=0)
+    assert eng2.n == 3000 and eng2.dim == 100 and eng2.dtype == dtype and eng2.ids[7] == "r7"
+    for algo in (("scan", "gemm") if dtype == "bfloat16" else ("scan",)):
+        r1, s1 = eng.search(q, 20, algo=algo)
+        r2, s2 = eng2.search(q, 20, algo=algo)
+        assert np.array_equal(r1, r2) and np.array_equal(s1, s2), algo
+    z = np.load(path)
+    assert z["data"].dtype == (np.uint16 if dtype == "bfloat16" else np.float32) and z["data"].shape == (3000, 100)
+    if dtype == "bfloat16":
+        assert np.array_equal(z["data"], (osr.to_bf16_round(g).view(np.uint32) >> 16).astype(np.uint16))
+    ids_a, sc_a = eng.retrieve(g[5], K=3)
+    ids_b, sc_b = eng2.retrieve(g[5], K=3)
+    assert ids_a == ids_b and sc_a == sc_b
