@@ -1,5 +1,17 @@
-"""Drop-in for the reference's ``Retrieval`` package (``Retrieval/__init__.py:1-3``)."""
-from .retrieval import B200RetrievalEngine, RetrievalEngine, make_retrieval_engine
-from .reranker import Reranker
+"""Drop-in for the reference's ``Retrieval`` package.
 
-__all__ = ["RetrievalEngine", "Reranker", "make_retrieval_engine", "B200RetrievalEngine"]
+The reference exports three names from here (``Retrieval/__init__.py:1-3``); the same three resolve to
+the B200 implementations: the engine factory and abstract engine (``retrieval.py``: exact search on the
+device behind the DLS engine's ``retrieve`` signature) and the label / knowledge-graph reranker
+(``reranker.py``: device tables + rerank kernels).  ``B200RetrievalEngine`` is exported in addition for
+callers that want the batched ``search`` entry point, ``save_blob`` / ``load_blob`` and ``from_arrays``.
+"""
+from . import reranker as _reranker
+from . import retrieval as _retrieval
+
+RetrievalEngine = _retrieval.RetrievalEngine
+B200RetrievalEngine = _retrieval.B200RetrievalEngine
+make_retrieval_engine = _retrieval.make_retrieval_engine
+Reranker = _reranker.Reranker
+
+__all__ = ("B200RetrievalEngine", "Reranker", "RetrievalEngine", "make_retrieval_engine")
