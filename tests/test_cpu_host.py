@@ -163,3 +163,24 @@ def test_label_attention_pooling_matches_reference_module(tmp_path):
     assert got.shape == (d,) and np.allclose(got, want.squeeze(0).numpy(), rtol=1e-5, atol=1e-6)
     rr.attn_params = Reranker._load_label_attention(tmp_path / "missing.pt", hidden)
     assert rr.attn_params is None and np.allclose(rr._pool(x.numpy()), x.numpy().mean(axis=0))
+
+
+def test_header_is_plain_c_and_links(tmp_path, lib):
+    """include/mmr_b200.h is a plain-C (C99) header -- no C++ / torch types in the signatures -- and a C
+    program links against libmmr_b200.so and calls it (no GPU needed for mmr_abi_version)."""
+    import shutil
+    import subprocess
+    from multi_modal_retrieval_predict_project_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "mmr_b200.h"\n'
+                   'int main(void) { return mmr_abi_version() == MMR_ABI_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    obj, exe = tmp_path / "t.o", tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o", str(obj)],
+                   check=True)
+    subprocess.run(["gcc", str(obj), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir,
+                    "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
