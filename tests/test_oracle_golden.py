@@ -182,3 +182,21 @@ def test_average_precision_restatement_matches_sklearn():
     res, table = ogt.label_ranking_eval(embs, vals, topk=(1, 5))
     assert set(res) == {"recall@1", "recall@5", "mAP"} and table.shape == (40, 3)
     assert abs(res["mAP"] - table[:, 0].mean()) < 1e-15 and np.all((table >= 0) & (table <= 1))
+
+
+def test_label_ranking_eval_matches_reference_golden():
+    """oracle.gt.label_ranking_eval == the reference's own evaluate_label_attention
+    (Trainner/train_label_attention.py:95-131, executed by tests/golden/make_golden.py with the reference's
+    LabelAttention module) on the recorded embeddings -- records with equal label sets have identical
+    embeddings, so the fixture also pins the tie behaviour of the ``np.argsort(-sim_row)`` the reference uses."""
+    import json
+    from pathlib import Path
+    from oracle import gt as ogt
+    golden = Path(__file__).resolve().parent / "golden"
+    z = np.load(golden / "label_ranking_inputs.npz")
+    want = json.load(open(golden / "label_ranking.json"))
+    got, table = ogt.label_ranking_eval(z["embs"], z["labels"], topk=(1, 5, 10))
+    assert set(got) == set(want)
+    for key, val in want.items():
+        assert abs(got[key] - val) < 1e-12, (key, got[key], val)
+    assert table.shape == (z["embs"].shape[0], 4)
