@@ -1,4 +1,4 @@
-"""Diagnostic: CUDA-event timing of the phases of the sharded step (torchrun --nproc-per-node N):
+"""Diagnostic: CUDA-event timing of the phases of the sharded step over the NCCL transport (torchrun --nproc-per-node N):
 search | local cosine | blob all-gather | merge+payload of this rank's query slice | rerank |
 apply order | result all-gathers, next to the whole retrieve_reranked() call and the replicated
 search_rerank() it replaced."""
@@ -16,18 +16,19 @@ rows, dim, b, k = int(os.environ.get("ROWS", 10_000_000)), 512, int(os.environ.g
 lo, hi = shard_bounds(rows, world, rank)
 g = bench.gen_rows(lo, hi, dim, bench.SEED, dev, torch.bfloat16)
 eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=lr, row_offset=lo, borrow=True, keep_host=False)
-s = ShardedSearcher(eng)
+s = ShardedSearcher(eng, use_peer=False)   # phase split of the NCCL transport
+sp = ShardedSearcher(eng)                    # NVLink peer-memory transport (whole call only)
 q = torch.randn((b, dim), device=dev).to(torch.bfloat16).float()
 masks = bench.gen_masks(0, rows + b, dev); kg = bench.gen_rows(0, rows + b, 300, bench.SEED + 700000, dev, torch.float32, normalize=True)
 rer = Reranker.from_tables(masks, kg, device=lr); del masks, kg
 q_rec = torch.arange(rows, rows + b, device=dev)
 for _ in range(3):
-    s.retrieve_reranked(rer, q, k, q_rec, topk=k); s.search_rerank(rer, q, k, q_rec, topk=k)
+    s.retrieve_reranked(rer, q, k, q_rec, topk=k); sp.retrieve_reranked(rer, q, k, q_rec, topk=k); s.search_rerank(rer, q, k, q_rec, topk=k)
 torch.cuda.synchronize()
 lib = _lib.load()
 names = ["search", "cosine", "allgather_blob", "merge_slice", "rerank_slice", "apply_order", "allgather_result"]
 tot = {n: 0.0 for n in names}
-whole = {"retrieve_reranked": 0.0, "search_rerank(replicated)": 0.0}
+whole = {"retrieve_reranked(nccl)": 0.0, "retrieve_reranked(peer)": 0.0, "search_rerank(replicated)": 0.0}
 per = (b + world - 1) // world
 q_lo, q_hi = min(b, rank * per), min(b, (rank + 1) * per)
 iters = 5
@@ -50,7 +51,8 @@ for it in range(iters):
     dist.all_gather_into_tensor(all_ids, my_ids); dist.all_gather_into_tensor(all_fin, my_fin); ev[7].record()
     torch.cuda.synchronize()
     for i, n in enumerate(names): tot[n] += ev[i].elapsed_time(ev[i + 1])
-    for name, fn in (("retrieve_reranked", lambda: s.retrieve_reranked(rer, q, k, q_rec, topk=k)),
+    for name, fn in (("retrieve_reranked(nccl)", lambda: s.retrieve_reranked(rer, q, k, q_rec, topk=k)),
+                     ("retrieve_reranked(peer)", lambda: sp.retrieve_reranked(rer, q, k, q_rec, topk=k)),
                      ("search_rerank(replicated)", lambda: s.search_rerank(rer, q, k, q_rec, topk=k))):
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
