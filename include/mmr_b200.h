@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMR_ABI_VERSION 1
+#define MMR_ABI_VERSION 2
 
 /* status codes */
 #define MMR_OK        0
@@ -56,6 +56,17 @@ extern "C" {
                               (dtype_in == dtype_store, row stride == d_pad): use it in place */
 
 #define MMR_MAX_K 1024
+
+/* mmr_index_tune knobs (per handle; they select among kernel instantiations that all return the same
+ * results -- the parity tests pin each of them explicitly, production code leaves them on AUTO) */
+#define MMR_TUNE_GEMM_VARIANT 0  /* value: MMR_GEMM_VARIANT_* */
+#define MMR_TUNE_GEMM_PARTS   1  /* value: 0 = automatic, > 0 = number of gallery parts per query tile */
+#define MMR_TUNE_GEMM_PAIR    2  /* value: MMR_GEMM_PAIR_* */
+#define MMR_GEMM_VARIANT_AUTO  0 /* short-launch variant for <= 2048 gallery tiles per part, else long-launch */
+#define MMR_GEMM_VARIANT_LONG  1 /* long-launch instantiation: lists fill and compact, lockstep start-up */
+#define MMR_GEMM_VARIANT_SHORT 2 /* short-launch instantiation: probe pass + pacing + bound-filtered final pass */
+#define MMR_GEMM_PAIR_AUTO 0     /* cta_group::2 CTA pairs whenever the batch has >= 2 query tiles */
+#define MMR_GEMM_PAIR_OFF  1     /* single-CTA (cta_group::1) instantiation */
 
 typedef struct mmr_index mmr_index;                 /* one gallery row-shard resident in HBM */
 typedef struct mmr_rerank_tables mmr_rerank_tables; /* label bitmasks + KG vectors in HBM   */
@@ -92,6 +103,15 @@ int mmr_index_get_rows(const mmr_index* index, const int64_t* rows, int64_t m, f
  * (or 1 again) synchronises, returns the summed duration in milliseconds and the number of timed
  * launches since the previous call (either pointer may be NULL), and resets the counters. */
 int mmr_index_profile(mmr_index* index, int32_t enable, double* kernel_ms_sum, int32_t* kernel_launches);
+
+/* Kernel selection of this handle's searches (MMR_TUNE_*); takes effect from the next mmr_search. */
+int mmr_index_tune(mmr_index* index, int32_t knob, int32_t value);
+/* What the most recent mmr_search on this handle ran: algo = MMR_ALGO_SCAN / MMR_ALGO_GEMM (0 before the
+ * first search); for the GEMM additionally variant = MMR_GEMM_VARIANT_LONG / _SHORT, pair = 1 for
+ * cta_group::2, the number of gallery parts and the gallery tiles (256 rows) per part.  Any pointer may be
+ * NULL.  The benchmark labels its roofline with this instead of guessing the dispatch. */
+int mmr_index_last_plan(const mmr_index* index, int32_t* algo, int32_t* variant, int32_t* pair, int32_t* n_parts,
+                        int32_t* tiles_per_part);
 
 /* ---------------------------------------------------------------------------------------
  * Exact cosine search + top-K.  Replaces the exact form cosine_similarity(Q, G) +

@@ -212,6 +212,28 @@ class B200RetrievalEngine(RetrievalEngine):
         _lib.check(self._lib.mmr_index_profile(self._handle, 1 if enable else 0, _lib.C.byref(ms), _lib.C.byref(cnt)))
         return ms.value, cnt.value
 
+    def tune(self, variant: Optional[str] = None, parts: Optional[int] = None, pair: Optional[bool] = None):
+        """Pin the GEMM kernel instantiation of this engine's searches (mmr_index_tune): ``variant``
+        ``"auto"`` | ``"long"`` | ``"short"``, ``parts`` = gallery parts per query tile (0 = automatic),
+        ``pair`` = use cta_group::2 CTA pairs.  All choices return the same results; the parity tests
+        run each of them explicitly."""
+        if variant is not None:
+            _lib.check(self._lib.mmr_index_tune(self._handle, _lib.TUNE_GEMM_VARIANT, _lib.GEMM_VARIANTS[variant]))
+        if parts is not None:
+            _lib.check(self._lib.mmr_index_tune(self._handle, _lib.TUNE_GEMM_PARTS, int(parts)))
+        if pair is not None:
+            _lib.check(self._lib.mmr_index_tune(self._handle, _lib.TUNE_GEMM_PAIR, 0 if pair else 1))
+        return self
+
+    def last_plan(self) -> dict:
+        """What the most recent search ran (mmr_index_last_plan): ``{"algo": "scan"|"gemm", "variant":
+        "long"|"short"|None, "pair": bool, "parts": int, "tiles_per_part": int}``."""
+        v = [_lib.C.c_int32() for _ in range(5)]
+        _lib.check(self._lib.mmr_index_last_plan(self._handle, *[_lib.C.byref(x) for x in v]))
+        algo = {0: None, _lib.ALGO_SCAN: "scan", _lib.ALGO_GEMM: "gemm"}[v[0].value]
+        return {"algo": algo, "variant": {0: None, 1: "long", 2: "short"}[v[1].value], "pair": bool(v[2].value),
+                "parts": v[3].value, "tiles_per_part": v[4].value}
+
     # -- batched search (the hot path) ----------------------------------------------------------
     def search(self, queries, K: int, exclude_rows=None, algo: Optional[str] = None, out_rows=None, out_scores=None):
         """Exact top-K for a batch.  ``queries``: numpy ``(B, D)`` / ``(D,)`` (host) or a torch
@@ -225,10 +247,7 @@ class B200RetrievalEngine(RetrievalEngine):
         K = int(K)
         if K < 1:
             raise ValueError("K must be >= 1")
-        name = algo if algo is not None else self.algo
-        if name == "auto":  # debugging aid: MMR_B200_ALGO=scan|gemm overrides the automatic choice
-            name = os.environ.get("MMR_B200_ALGO", "auto")
-        a = _lib.ALGOS[name]
+        a = _lib.ALGOS[algo if algo is not None else self.algo]
         on_device = _is_tensor(queries) and queries.is_cuda
         if _is_tensor(queries):
             q = queries.detach()

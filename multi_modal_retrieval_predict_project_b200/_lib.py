@@ -19,7 +19,10 @@ MMR_F32, MMR_BF16 = 0, 1
 ALGO_AUTO, ALGO_SCAN, ALGO_GEMM = 0, 1, 2
 FLAG_BORROW = 1
 MAX_K = 1024
-ABI_VERSION = 1
+ABI_VERSION = 2
+
+TUNE_GEMM_VARIANT, TUNE_GEMM_PARTS, TUNE_GEMM_PAIR = 0, 1, 2
+GEMM_VARIANTS = {"auto": 0, "long": 1, "short": 2}
 
 ALGOS = {"auto": ALGO_AUTO, "scan": ALGO_SCAN, "gemm": ALGO_GEMM}
 
@@ -33,6 +36,8 @@ SIGNATURES = {
     "mmr_last_error": [],
     "mmr_launch_count": [],
     "mmr_index_profile": [_vp, _i32, C.POINTER(_f64), C.POINTER(_i32)],
+    "mmr_index_tune": [_vp, _i32, _i32],
+    "mmr_index_last_plan": [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)],
     "mmr_index_create": [C.POINTER(_vp), _vp, _i64, _i32, _i32, _i32, _i64, _i32, _i32, _vp],
     "mmr_index_destroy": [_vp],
     "mmr_index_info": [_vp, C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),

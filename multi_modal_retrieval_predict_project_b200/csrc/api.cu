@@ -25,7 +25,16 @@ struct mmr_index {
   void* emb = nullptr;
   bool owns_emb = true;
   float* inv_norm = nullptr;
-  std::mutex mu;  // search is re-entrant per handle by serialising on the handle's workspaces
+  // Re-entrancy: the grow-only workspaces below are one set per handle.  `mu` serialises the host side of
+  // a call; `last_done` (recorded at the end of every call on its stream) makes the NEXT call's stream
+  // wait for the previous call's kernels, so two threads / streams sharing one handle never overlap on
+  // the device either (calls with host outputs synchronise anyway).
+  std::mutex mu;
+  cudaEvent_t last_done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  mmr::GemmTune tune;
+  int last_algo = 0, last_variant = 0, last_pair = 0, last_parts = 0, last_tiles_per_part = 0;
   mmr::DeviceBuf q_in, q_store, q_f32, q_inv, scratch, excl_in, excl_local, partial, counts, tau_pub, out_scores, out_rows;
   // live kernel timing (mmr_index_profile)
   bool profiling = false;
@@ -46,8 +55,12 @@ namespace mmr {
 
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
-// MMR_B200_NO_TAU_SHARE=1 disables the cross-CTA threshold exchange of the GEMM path (A/B testing)
+#ifdef MMR_DIAG
+// diagnostic builds: MMR_B200_NO_TAU_SHARE=1 disables the cross-CTA threshold exchange of the GEMM path
 static const bool g_share_tau = std::getenv("MMR_B200_NO_TAU_SHARE") == nullptr;
+#else
+constexpr bool g_share_tau = true;
+#endif
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
@@ -230,6 +243,19 @@ __global__ void globalize_exclude_kernel(const int64_t* __restrict__ in, int b, 
   }
 }
 
+// Device-side ordering of consecutive calls on one handle (see mmr_index::mu): call under the mutex.
+int enter_call(mmr_index* ix, cudaStream_t stream) {
+  if (ix->has_last && ix->last_stream != stream) MMR_CUDA_TRY(cudaStreamWaitEvent(stream, ix->last_done, 0));
+  return MMR_OK;
+}
+int leave_call(mmr_index* ix, cudaStream_t stream) {
+  if (ix->last_done == nullptr) MMR_CUDA_TRY(cudaEventCreateWithFlags(&ix->last_done, cudaEventDisableTiming));
+  MMR_CUDA_TRY(cudaEventRecord(ix->last_done, stream));
+  ix->last_stream = stream;
+  ix->has_last = true;
+  return MMR_OK;
+}
+
 }  // namespace
 }  // namespace mmr
 
@@ -261,12 +287,47 @@ int mmr_index_profile(mmr_index* ix, int32_t enable, double* kernel_ms_sum, int3
   return MMR_OK;
 }
 
+int mmr_index_tune(mmr_index* ix, int32_t knob, int32_t value) {
+  MMR_REQUIRE(ix != nullptr, "mmr_index_tune: index is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  switch (knob) {
+    case MMR_TUNE_GEMM_VARIANT:
+      MMR_REQUIRE(value >= MMR_GEMM_VARIANT_AUTO && value <= MMR_GEMM_VARIANT_SHORT, "mmr_index_tune: bad GEMM variant");
+      ix->tune.variant = value;
+      return MMR_OK;
+    case MMR_TUNE_GEMM_PARTS:
+      MMR_REQUIRE(value >= 0, "mmr_index_tune: parts must be >= 0");
+      ix->tune.parts = value;
+      return MMR_OK;
+    case MMR_TUNE_GEMM_PAIR:
+      MMR_REQUIRE(value == MMR_GEMM_PAIR_AUTO || value == MMR_GEMM_PAIR_OFF, "mmr_index_tune: bad pair mode");
+      ix->tune.pair = value;
+      return MMR_OK;
+    default:
+      return fail(MMR_EINVAL, "mmr_index_tune: unknown knob " + std::to_string(knob));
+  }
+}
+
+int mmr_index_last_plan(const mmr_index* ix, int32_t* algo, int32_t* variant, int32_t* pair, int32_t* n_parts,
+                        int32_t* tiles_per_part) {
+  MMR_REQUIRE(ix != nullptr, "mmr_index_last_plan: index is NULL");
+  if (algo) *algo = ix->last_algo;
+  if (variant) *variant = ix->last_variant;
+  if (pair) *pair = ix->last_pair;
+  if (n_parts) *n_parts = ix->last_parts;
+  if (tiles_per_part) *tiles_per_part = ix->last_tiles_per_part;
+  return MMR_OK;
+}
+
 int mmr_index_create(mmr_index** out, const void* emb, int64_t n, int32_t d, int32_t dtype_in, int32_t dtype_store,
                      int64_t row_offset, int32_t device, int32_t flags, void* stream_v) {
   MMR_REQUIRE(out != nullptr, "mmr_index_create: out is NULL");
   *out = nullptr;
   MMR_REQUIRE(n >= 0 && d >= 1, "mmr_index_create: need n >= 0 and d >= 1");
   MMR_REQUIRE(n < 0xFFFFFFFFll, "mmr_index_create: a shard holds at most 2^32-2 rows");
+  // the cross-shard merge packs GLOBAL row ids into the low 32 bits of its ordering keys
+  MMR_REQUIRE(row_offset >= 0 && row_offset + n < 0xFFFFFFFFll,
+              "mmr_index_create: global row ids (row_offset + n) must stay below 2^32-1");
   MMR_REQUIRE(dtype_in == MMR_F32 || dtype_in == MMR_BF16, "mmr_index_create: dtype_in must be MMR_F32 or MMR_BF16");
   MMR_REQUIRE(dtype_store == MMR_F32 || dtype_store == MMR_BF16, "mmr_index_create: bad dtype_store");
   MMR_REQUIRE(emb != nullptr || n == 0, "mmr_index_create: emb is NULL");
@@ -364,6 +425,7 @@ int mmr_index_destroy(mmr_index* ix) {
     b->release();
   for (cudaEvent_t e : ix->ev_start) cudaEventDestroy(e);
   for (cudaEvent_t e : ix->ev_stop) cudaEventDestroy(e);
+  if (ix->last_done != nullptr) cudaEventDestroy(ix->last_done);
   delete ix;
   return MMR_OK;
 }
@@ -417,6 +479,7 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
   std::lock_guard<std::mutex> lock(ix->mu);
   DeviceGuard guard(ix->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MMR_TRY(enter_call(ix, stream));
 
   // queries -> storage dtype (bf16 index: round to bf16) padded to d_pad, + inverse norms
   const void* d_q = nullptr;
@@ -475,7 +538,12 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
   if (use == MMR_ALGO_GEMM) {
     GemmPlan gp;
     const int k_eff = k + (d_excl != nullptr ? 1 : 0);  // the excluded row is dropped by the select step
-    MMR_TRY(plan_gemm(ix->n, ix->d_pad, b, k_eff, ix->num_sms, &gp));
+    MMR_TRY(plan_gemm(ix->n, ix->d_pad, b, k_eff, ix->num_sms, ix->tune, &gp));
+    ix->last_algo = MMR_ALGO_GEMM;
+    ix->last_variant = gp.probe ? MMR_GEMM_VARIANT_SHORT : MMR_GEMM_VARIANT_LONG;
+    ix->last_pair = gp.pair;
+    ix->last_parts = gp.n_parts;
+    ix->last_tiles_per_part = gp.tiles_per_part;
     MMR_TRY(ix->partial.ensure(gp.cand_bytes));
     MMR_TRY(ix->counts.ensure(gp.count_bytes));
     MMR_TRY(ix->tau_pub.ensure(gp.pub_bytes));
@@ -501,6 +569,9 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     }
     ScanPlan sp;
     MMR_TRY(plan_scan(ix->n, ix->d_pad, ix->dtype, b, k, ix->num_sms, &sp));
+    ix->last_algo = MMR_ALGO_SCAN;
+    ix->last_variant = ix->last_pair = ix->last_tiles_per_part = 0;
+    ix->last_parts = sp.n_parts;
     MMR_TRY(ix->partial.ensure(sp.partial_bytes));
     if (ev0) MMR_CUDA_TRY(cudaEventRecord(ev0, stream));
     MMR_TRY(launch_scan(ix->emb, ix->dtype, ix->inv_norm, ix->n, ix->d_pad, q_f32, ix->q_inv.as<float>(), b, k, d_excl,
@@ -517,7 +588,7 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     MMR_CUDA_TRY(cudaMemcpyAsync(out_rows, d_rows, static_cast<size_t>(b) * k * sizeof(int64_t),
                                  cudaMemcpyDeviceToHost, stream));
   if (host_scores || host_rows) MMR_CUDA_TRY(cudaStreamSynchronize(stream));
-  return MMR_OK;
+  return leave_call(ix, stream);
 }
 
 int mmr_merge_topk_strided(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in,
@@ -828,6 +899,7 @@ int mmr_first_relevant_rank(mmr_index* ix, const void* q, int32_t b, int32_t q_d
   std::lock_guard<std::mutex> lock(ix->mu);
   DeviceGuard guard(ix->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MMR_TRY(enter_call(ix, stream));
   // queries -> storage dtype (rounded like mmr_search) -> fp32 padded + inverse norms
   const void* d_q = nullptr;
   MMR_TRY(stage_in(q, static_cast<size_t>(b) * ix->d * elem_size(q_dtype), ix->q_in, stream, &d_q));
@@ -852,7 +924,8 @@ int mmr_first_relevant_rank(mmr_index* ix, const void* q, int32_t b, int32_t q_d
   MMR_TRY(cs.out(out_total, static_cast<size_t>(b), &d_total));
   MMR_TRY(launch_first_relevant_rank(ix->emb, ix->dtype, ix->inv_norm, ix->n, ix->d_pad, q_f32, ix->q_inv.as<float>(), b,
                                      d_qm, d_gm, label_words, d_rank, d_total, stream));
-  return cs.finish();
+  MMR_TRY(cs.finish());
+  return leave_call(ix, stream);
 }
 
 int mmr_label_ranking_eval(const float* emb, const float* norms, int32_t n, int32_t d, const uint64_t* label_masks,

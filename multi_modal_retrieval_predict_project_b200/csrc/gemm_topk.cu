@@ -408,6 +408,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   // kernel traps loudly if the runtime did not honour it (no slack bytes are budgeted).
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+#ifndef MMR_DIAG
+  debug_flags = 0;  // the diagnostic switches exist only in -DMMR_DIAG builds
+#endif
   const int num_kc = d_pad / kBlockK;
   constexpr int kBStage = kPair ? kBBytes / 2 : kBBytes;  // gallery bytes this CTA stages per chunk
   constexpr int kStageBytes = kResident ? kBStage : kABytes + kBStage;
@@ -913,17 +916,31 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int d_pad, int b
   return MMR_OK;
 }
 
+#ifdef MMR_DIAG
+// Diagnostic build only (-DMMR_DIAG, scripts/*): environment overrides for A/B experiments.  The shipping
+// library reads no environment variable on the search path.
+int diag_env(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v != nullptr ? std::atoi(v) : dflt;
+}
+#endif
+
 }  // namespace
 
-int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
-  if (k < 1 || k > MMR_MAX_K) return fail(MMR_EUNSUP, "gemm: k must be in [1, 1024]");
+int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, const GemmTune& tune, GemmPlan* plan) {
+  // k + 1 candidates are kept when a row is excluded per query (dropped again by the select step)
+  if (k < 1 || k > MMR_MAX_K + 1) return fail(MMR_EUNSUP, "gemm: k must be in [1, 1024]");
   if (n < 1) return fail(MMR_EINVAL, "gemm: empty gallery");
   if (d_pad % kBlockK != 0) return fail(MMR_EINVAL, "gemm: d_pad must be a multiple of 64");
   const int m_tiles = (b + kBlockM - 1) / kBlockM;
   const int64_t tiles_total = (n + kBlockN - 1) / kBlockN;
-  // CTA pairs (cta_group::2) whenever there are at least two query tiles; MMR_B200_GEMM_PAIR=0 disables
-  static const bool pair_env = std::getenv("MMR_B200_GEMM_PAIR") == nullptr || std::atoi(std::getenv("MMR_B200_GEMM_PAIR")) != 0;
-  const bool pair = pair_env && m_tiles >= 2;
+  // CTA pairs (cta_group::2) whenever there are at least two query tiles
+  bool pair_ok = tune.pair != MMR_GEMM_PAIR_OFF;
+#ifdef MMR_DIAG
+  static const bool pair_env = diag_env("MMR_B200_GEMM_PAIR", 1) != 0;
+  pair_ok = pair_ok && pair_env;
+#endif
+  const bool pair = pair_ok && m_tiles >= 2;
   const int ctas_per_unit = pair ? 2 : 1;
   const int m_units = pair ? (m_tiles + 1) / 2 : m_tiles;   // scheduling units along the batch
   const int slots = num_sms / ctas_per_unit;                // units resident at once
@@ -943,6 +960,7 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
     }
     if (eff >= 0.97 || parts == tiles_total) break;
   }
+  if (tune.parts > 0) best_parts = static_cast<int>(tune.parts < tiles_total ? tune.parts : tiles_total);
   const int tiles_per_part = static_cast<int>((tiles_total + best_parts - 1) / best_parts);
   const int n_parts = static_cast<int>((tiles_total + tiles_per_part - 1) / tiles_per_part);
   int cap = 512;
@@ -960,6 +978,24 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan) {
   }
   plan->tiles_per_part = tiles_per_part;
   plan->cap = cap;
+  // Short launches (<= 2048 tiles per part: the shards at N >= 4, cfg2, cfg5) run the kProbe kernel:
+  // the ~300 us per-wave warm-up it removes is 10-25 % of such a launch.  Long launches keep the original
+  // start-up: its lockstep compactions keep the sharers of a gallery part aligned for the whole launch
+  // (ncu at 10M x 4096: L2 hit 78 % / 28.8 GB of DRAM reads, vs 68 % / 36.2 GB with probe + pacing)
+  // and the warm-up is < 2 % there.  mmr_index_tune(MMR_TUNE_GEMM_VARIANT) pins either instantiation.
+  {
+    int probe_max = 2048;
+#ifdef MMR_DIAG
+    static const int probe_max_env = diag_env("MMR_B200_GEMM_PROBE_MAX_TILES", 2048);
+    probe_max = probe_max_env;
+#endif
+    const int tiles_last = static_cast<int>(tiles_total) - (n_parts - 1) * tiles_per_part;
+    // the probe needs every list of the launch to get at least one tile (else its bound is never published)
+    const bool probe_ok = tiles_per_part >= kEpiGroups && tiles_last >= kEpiGroups;
+    const bool want = tune.variant == MMR_GEMM_VARIANT_SHORT ||
+                      (tune.variant == MMR_GEMM_VARIANT_AUTO && tiles_per_part <= probe_max);
+    plan->probe = (want && probe_ok) ? 1 : 0;
+  }
   plan->cand_bytes = static_cast<size_t>(b) * plan->n_lists * cap * sizeof(uint2);
   plan->count_bytes = static_cast<size_t>(b) * plan->n_lists * sizeof(int32_t);
   // published pruning bounds [n_lists][m_tiles * 128] followed by one pacing counter per scheduling unit
@@ -983,36 +1019,32 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   const int tiles_total = static_cast<int>((n + kBlockN - 1) / kBlockN);
   const int m_units = pair ? (plan.m_tiles + 1) / 2 : plan.m_tiles;
   const int grid = ((m_units + plan.m_group - 1) / plan.m_group) * plan.m_group * plan.n_parts * (pair ? 2 : 1);
-  const int tiles_last = tiles_total - (plan.n_parts - 1) * plan.tiles_per_part;
-  static const int probe_max_env =
-      std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES") ? std::atoi(std::getenv("MMR_B200_GEMM_PROBE_MAX_TILES")) : 2048;
-  // short launch, and every list of the launch gets at least one tile (else its bound is never published)
-  const bool probe = plan.tiles_per_part <= probe_max_env && plan.tiles_per_part >= kEpiGroups && tiles_last >= kEpiGroups;
+  const bool probe = plan.probe != 0;
   auto kern = probe ? (pair ? (sp.resident ? gemm_topk_kernel<true, true, true> : gemm_topk_kernel<false, true, true>)
                             : (sp.resident ? gemm_topk_kernel<true, false, true> : gemm_topk_kernel<false, false, true>))
                     : (pair ? (sp.resident ? gemm_topk_kernel<true, true, false> : gemm_topk_kernel<false, true, false>)
                             : (sp.resident ? gemm_topk_kernel<true, false, false> : gemm_topk_kernel<false, false, false>));
   MMR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sp.total)));
   // threshold exchange: rank published per part and refresh period (in gallery tiles)
-  // MMR_B200_GEMM_DEBUG bit 0: skip the epilogue's score processing (results are garbage) to
-  // measure the TMA + MMA pipeline alone
-  static const int debug_flags = std::getenv("MMR_B200_GEMM_DEBUG") ? std::atoi(std::getenv("MMR_B200_GEMM_DEBUG")) : 0;
   const int pub_rank = (k + plan.n_lists - 1) / plan.n_lists;
   // every 4th tile of a warpgroup is enough (the bound only tightens; a stale value just prunes less)
   const int refresh = plan.n_lists <= 64 ? 2 : 2 * ((plan.n_lists + 63) / 64);
   // Early per-tile refresh: measured +28 % at 1M x 1024 (8 CTAs share a gallery part) but -15 % at
   // 1M x 2048/4096 (16 sharers): without the synchronous first compaction the sharers drift apart
-  // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).  MMR_B200_EARLY_TILES overrides.
-  static const int early_env = std::getenv("MMR_B200_EARLY_TILES") ? std::atoi(std::getenv("MMR_B200_EARLY_TILES")) : -1;
-  // Short launches (<= 2048 tiles per part: the shards at N >= 4, cfg2, cfg5) run the kProbe kernel:
-  // the ~300 us per-wave warm-up it removes is 10-25 % of such a launch.  Long launches keep the original
-  // start-up: its lockstep compactions keep the sharers of a gallery part aligned for the whole launch
-  // (ncu at 10M x 4096: L2 hit 78 % / 28.8 GB of DRAM reads, vs 68 % / 36.2 GB with probe + pacing)
-  // and the warm-up is < 2 % there.  MMR_B200_GEMM_PROBE_MAX_TILES / MMR_B200_GEMM_PACE override.
-  static const int pace_env = std::getenv("MMR_B200_GEMM_PACE") ? std::atoi(std::getenv("MMR_B200_GEMM_PACE")) : -1;
-  const int pace_w = pace_env >= 0 ? pace_env : 64;  // only read by the kProbe kernel
-  const int early_tiles = early_env >= 0 ? early_env : (plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0);
-  const int flags = debug_flags;  // bit 0: skip the score processing, bit 1: no probe pass in the kProbe kernel
+  // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).
+  int early_tiles = plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0;
+  int pace_w = 64;  // only read by the kProbe kernel
+  int flags = 0;    // diagnostic builds: bit 0 skips the score processing, bit 1 the probe pass
+#ifdef MMR_DIAG
+  // MMR_B200_GEMM_DEBUG bit 0: skip the epilogue's score processing (results are garbage) to measure the
+  // TMA + MMA pipeline alone; MMR_B200_EARLY_TILES / MMR_B200_GEMM_PACE override the heuristics above
+  static const int debug_env = diag_env("MMR_B200_GEMM_DEBUG", 0);
+  static const int early_env = diag_env("MMR_B200_EARLY_TILES", -1);
+  static const int pace_env = diag_env("MMR_B200_GEMM_PACE", -1);
+  flags = debug_env;
+  if (early_env >= 0) early_tiles = early_env;
+  if (pace_env >= 0) pace_w = pace_env;
+#endif
   if (tau_pub != nullptr) MMR_CUDA_TRY(cudaMemsetAsync(tau_pub, 0, plan.pub_bytes, stream));
   // a list whose warpgroup gets no tile (single-tile parts) must still report an empty list
   MMR_CUDA_TRY(cudaMemsetAsync(counts, 0, plan.count_bytes, stream));

@@ -77,9 +77,17 @@ int launch_apply_order(const int64_t* rows, const int32_t* order, const double* 
                        int64_t* out_rows, double* out_final, cudaStream_t stream);
 
 // gemm_topk.cu: tcgen05 GEMM + fused top-K (bf16 storage).
+// Per-handle tuning (mmr_index_tune): the defaults are the production choice; tests pin each kernel
+// instantiation explicitly instead of relying on the size heuristics.
+struct GemmTune {
+  int variant = MMR_GEMM_VARIANT_AUTO;  // MMR_GEMM_VARIANT_*: which start-up / pruning variant of the kernel runs
+  int parts = 0;                        // > 0: force this many gallery parts (clamped to the tile count)
+  int pair = MMR_GEMM_PAIR_AUTO;        // MMR_GEMM_PAIR_*: cta_group::2 CTA pairs or single CTAs
+};
 struct GemmPlan {
   int m_tiles;          // query tiles of 128
   int pair;             // 1 = cta_group::2 (a 2-CTA cluster works on two query tiles x one gallery tile)
+  int probe;            // 1 = the short-launch (kProbe) instantiation runs
   int m_group;          // query tiles (pairs in pair mode) scheduled together: one wave = m_group x n_parts units
   int n_parts;          // gallery parts (CTAs per query tile)
   int n_lists;          // candidate lists per query (parts x epilogue warpgroups)
@@ -89,7 +97,7 @@ struct GemmPlan {
   size_t count_bytes;   // per-(query, list) counts
   size_t pub_bytes;     // per-(list, query) published pruning thresholds
 };
-int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, GemmPlan* plan);
+int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, const GemmTune& tune, GemmPlan* plan);
 int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int d_pad, const void* q_bf16,
                      const float* q_inv, int b, int k, const int64_t* exclude_local, const GemmPlan& plan,
                      uint64_t* cand, int32_t* counts, uint32_t* tau_pub, cudaStream_t stream);

@@ -23,32 +23,46 @@ _SRC = os.path.join(REFERENCE_ROOT, "src")
 
 
 def reference_available() -> bool:
+    """The full reference checkout is mounted (authoring container)."""
     return os.path.isfile(os.path.join(_SRC, "Retrieval", "retrieval.py"))
+
+
+def staged_available() -> bool:
+    """The hot-path files packed by ``oracle/stage_ref.py`` are present (the archive travels to the GPU box)."""
+    from .stage_ref import ARCHIVE
+    return os.path.isfile(ARCHIVE)
 
 
 _loaded = None
 
 
-def load_reference():
+def load_reference(allow_staged: bool = False):
     """Return a namespace with the reference's hot-path symbols.
 
     Attributes: ``make_retrieval_engine``, ``RetrievalEngine``, ``DLSRetrievalEngine``,
     ``Reranker``, ``metrics`` (the ``Helpers.retrieval_metrics`` module),
-    ``LabelAttention``.
+    ``LabelAttention``, ``root`` (where the files were loaded from).
+    With ``allow_staged`` the copies under ``oracle/_ref`` are used when ``/root/reference`` is absent
+    (the GPU box); they are the same files, byte for byte (``oracle/_ref/MANIFEST.json``).
     """
     global _loaded
     if _loaded is not None:
         return _loaded
-    if not reference_available():
+    if reference_available():
+        src = _SRC
+    elif allow_staged and staged_available():
+        from .stage_ref import staged_root
+        src = os.path.join(staged_root(), "src")
+    else:
         raise RuntimeError(f"reference not present under {REFERENCE_ROOT}")
     sys.dont_write_bytecode = True
     for pkg in ("KnowledgeGraph", "Helpers"):
         if pkg not in sys.modules:
             m = types.ModuleType(pkg)
-            m.__path__ = [os.path.join(_SRC, pkg)]
+            m.__path__ = [os.path.join(src, pkg)]
             sys.modules[pkg] = m
-    if _SRC not in sys.path:
-        sys.path.insert(0, _SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import importlib
 
     retrieval = importlib.import_module("Retrieval.retrieval")
@@ -64,6 +78,7 @@ def load_reference():
         LabelAttention=la.LabelAttention,
         retrieval_module=retrieval,
         reranker_module=reranker,
+        root=os.path.dirname(src),
     )
     _loaded = ns
     return ns

@@ -188,3 +188,61 @@ class OracleReranker:
             ranked = ranked[:topk]
         return [(candidate_ids[i], float(final[i]), float(emb_n[i]), float(lab_n[i]),
                  float(kg_n[i])) for i in ranked]
+
+
+def rerank_from_arrays(q_emb, cand_embs, q_mask, cand_masks, q_kg, cand_kg, alpha=0.6, beta=0.25, gamma=0.15,
+                       topk=None, emb_scores=None):
+    """The scoring half of ``Reranker.rerank`` (reference ``reranker.py:298-329``) on pre-resolved arrays --
+    what the table-driven device path (``Reranker.from_tables``: integer label masks, KG rows) computes:
+    ``emb_scores[i] = safe_cos(q_emb, cand_embs[i])`` (``:298``; or the supplied ``emb_scores``),
+    Jaccard of the label sets encoded by the masks' bits (``:301-304``), ``safe_cos`` of the KG rows
+    (``:307-319``), min-max each (``:322-324``), ``final = alpha*e + beta*l + gamma*g`` (``:325``), order by
+    final descending (``:327``; ties by candidate position ascending).  Returns ``[(position, final, emb_n,
+    lab_n, kg_n)]``."""
+    n = len(cand_masks)
+
+    def bits(m):
+        m = int(m)
+        return {i for i in range(m.bit_length()) if (m >> i) & 1}
+
+    if emb_scores is None:
+        emb_scores = [safe_cos(q_emb, cand_embs[i]) for i in range(n)]
+    else:
+        emb_scores = [float(x) for x in emb_scores]
+    ql = bits(q_mask)
+    lab_scores = [jaccard_sets(ql, bits(cand_masks[i])) for i in range(n)]
+    kg_scores = [safe_cos(q_kg, cand_kg[i]) for i in range(n)]
+    emb_n = np.array(minmax_scale_list(emb_scores))
+    lab_n = np.array(minmax_scale_list(lab_scores))
+    kg_n = np.array(minmax_scale_list(kg_scores))
+    final = alpha * emb_n + beta * lab_n + gamma * kg_n
+    ranked = np.lexsort((np.arange(n), -final))
+    if topk:
+        ranked = ranked[:topk]
+    return [(int(i), float(final[i]), float(emb_n[i]), float(lab_n[i]), float(kg_n[i])) for i in ranked]
+
+
+def reranked_lists_match(got_ids, got_final, cand_ids, want, rtol=1e-5, atol=2e-6):
+    """Compare one query's device result (ids + combined scores, best first) with ``want`` from
+    :func:`rerank_from_arrays` (positions into ``cand_ids``): finals within tolerance position by
+    position; ids equal except for swaps between (near-)equal finals.  Returns ``(ok, why)``."""
+    if len(got_ids) != len(want):
+        return False, f"length {len(got_ids)} vs {len(want)}"
+    for r, (gid, gf, w) in enumerate(zip(got_ids, got_final, want)):
+        if abs(float(gf) - w[1]) > atol + rtol * abs(w[1]):
+            return False, f"rank {r}: final {float(gf)!r} vs {w[1]!r}"
+    want_ids = [int(cand_ids[w[0]]) for w in want]
+    if sorted(int(x) for x in got_ids) != sorted(want_ids):
+        # a swap at the cut (topk < candidates) between near-equal finals is allowed
+        extra = set(int(x) for x in got_ids) ^ set(want_ids)
+        fin_of = {int(cand_ids[w[0]]): w[1] for w in want}
+        cut = want[-1][1]
+        for e in extra:
+            if e in fin_of and abs(fin_of[e] - cut) > atol + rtol * abs(cut):
+                return False, f"id {e} is not a near-tie at the cut"
+    for r, (gid, w) in enumerate(zip(got_ids, want)):
+        if int(gid) != int(cand_ids[w[0]]):
+            # the id found at rank r must have (near-)the same final as the expected one
+            if abs(float(got_final[r]) - w[1]) > atol + rtol * abs(w[1]):
+                return False, f"rank {r}: id {int(gid)} vs {int(cand_ids[w[0]])} (not a tie)"
+    return True, "ok"

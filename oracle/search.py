@@ -63,10 +63,16 @@ def exact_topk(q: np.ndarray, g: np.ndarray, k: int) -> Tuple[np.ndarray, np.nda
     kk = min(int(k), n)
     rows = np.empty((sim.shape[0], kk), dtype=np.int64)
     scores = np.empty((sim.shape[0], kk), dtype=sim.dtype)
-    ar = np.arange(n)
     for i in range(sim.shape[0]):
-        # lexsort: last key is primary.  primary = -score (desc), secondary = row (asc)
-        order = np.lexsort((ar, -sim[i].astype(np.float64)))[:kk]
+        # every row scoring at least the kk-th largest value (all boundary ties included), then
+        # lexsort (last key is primary): primary = -score (desc), secondary = row (asc).  Identical to
+        # sorting the whole row, without the O(N log N) per query.
+        if kk < n:
+            thr = np.partition(sim[i], n - kk)[n - kk]
+            idx = np.nonzero(sim[i] >= thr)[0]
+        else:
+            idx = np.arange(n)
+        order = idx[np.lexsort((idx, -sim[i, idx].astype(np.float64)))[:kk]]
         rows[i] = order
         scores[i] = sim[i, order]
     return rows, scores

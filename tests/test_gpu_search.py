@@ -254,6 +254,130 @@ def test_gemm_large_k_generic_compaction():
         _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
 
 
+# ---------------------------------------------------------------------------------------------------
+# Both GEMM instantiations, pinned per engine (mmr_index_tune), on launches long enough (>= 200 gallery
+# tiles per part) that lists fill and compact, the cross-list bound is refreshed many times and the final
+# per-list pass has real work -- the regime of the headline launch (4341 tiles per part at 10M rows).
+# ---------------------------------------------------------------------------------------------------
+def _tuned_search(eng, q, k, variant, parts, pair=True, min_tiles=200):
+    eng.tune(variant=variant, parts=parts, pair=pair)
+    rows, scores = eng.search(q, k, algo="gemm")
+    plan = eng.last_plan()
+    assert plan["algo"] == "gemm" and plan["variant"] == variant, plan
+    assert plan["tiles_per_part"] >= min_tiles, plan
+    return rows, scores, plan
+
+
+@pytest.mark.parametrize("variant", ["long", "short"])
+@pytest.mark.parametrize("n,d,b,k,parts", [(120_000, 128, 300, 100, 2),    # 2 CTA pairs x 2 parts, odd tile count
+                                           (150_001, 64, 100, 100, 1),     # single-CTA instantiation, ragged last tile
+                                           (260_000, 512, 700, 100, 4),    # resident-Q pairs at d = 512, 3 pair units
+                                           (110_000, 1024, 260, 10, 2)])   # streamed-Q pairs
+def test_gemm_variants_many_tiles_per_part(variant, n, d, b, k, parts):
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=131))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=132))
+    eng = _engine(g, dtype="bfloat16", keep_host=False)
+    rows, scores, plan = _tuned_search(eng, q, k, variant, parts)
+    assert plan["pair"] == (b > 128) and plan["parts"] == parts
+    want_rows, want_scores = osr.exact_topk(q, g, k)
+    _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+    # the two instantiations agree bit for bit (same accumulation order, same ordering rule)
+    other = "short" if variant == "long" else "long"
+    rows2, scores2, _ = _tuned_search(eng, q, k, other, parts)
+    assert np.array_equal(rows, rows2) and np.array_equal(scores, scores2)
+
+
+@pytest.mark.parametrize("variant", ["long", "short"])
+@pytest.mark.parametrize("pair", [True, False])
+def test_gemm_variants_duplicates_across_compactions(variant, pair):
+    """More exact-score ties than k, spread over gallery tiles that sit hundreds of tiles apart (so the
+    copies reach a list before and after several compactions, and through both warpgroups' lists):
+    the winners are the lowest row ids; zero rows / zero queries score exactly 0."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    n, d, b, k = 70_000, 128, 200, 50
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=141))
+    dup = np.r_[100:130, 20_000:20_030, 45_000:45_040, 69_950:69_990]
+    g[dup] = g[7]
+    g[1000] = 0.0
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=142))
+    q[3] = g[7]
+    q[5] = 0.0
+    q[130] = g[7] * 2.0            # second query tile
+    eng = _engine(g, dtype="bfloat16", keep_host=False)
+    rows, scores, plan = _tuned_search(eng, q, k, variant, 1, pair=pair)
+    assert plan["pair"] == pair and plan["parts"] == 1
+    for qi in (3, 130):
+        assert rows[qi, 0] == 7 and np.array_equal(rows[qi, 1:50], np.sort(dup)[:49]), (variant, qi)
+    assert np.all(scores[5] == 0.0) and np.array_equal(rows[5], np.arange(50))
+    want_rows, want_scores = osr.exact_topk(q, g, k)
+    _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("variant", ["long", "short"])
+def test_gemm_variants_large_k(variant):
+    """k > 128 / > 256 (1024- and 4096-entry lists, generic compaction) on >= 200 tiles per part."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(120_000, 128, seed=151))
+    q = osr.to_bf16_round(synth.make_embeddings(20, 128, seed=152))
+    eng = _engine(g, dtype="bfloat16", keep_host=False)
+    for k in (200, 300, 1000):
+        rows, scores, _ = _tuned_search(eng, q, k, variant, 2)
+        want_rows, want_scores = osr.exact_topk(q, g, k)
+        _check(rows, scores, want_rows, want_scores, rtol=2e-5, atol=1e-6)
+
+
+def test_exclusion_at_max_k_and_tune_errors():
+    """exclude_rows with k = MMR_MAX_K keeps k + 1 candidates inside the GEMM (ADVICE: it used to be
+    rejected); unknown knobs / values are MMR_EINVAL."""
+    from multi_modal_retrieval_predict_project_b200 import _lib, synth
+    g = osr.to_bf16_round(synth.make_embeddings(5000, 64, seed=161))
+    eng = _engine(g, dtype="bfloat16")
+    q = g[:6]
+    ex = np.arange(6, dtype=np.int64)
+    rows, scores = eng.search(q, 1024, exclude_rows=ex, algo="gemm")
+    sim = osr.cosine_similarity(q, g)
+    sim[np.arange(6), ex] = -np.inf
+    for i in range(6):
+        order = np.lexsort((np.arange(5000), -sim[i].astype(np.float64)))[:1024]
+        ok, why = osr.topk_matches(rows[i], scores[i], order, sim[i, order], rtol=2e-5, atol=1e-6)
+        assert ok, (i, why)
+    lib = _lib.load()
+    assert lib.mmr_index_tune(eng._handle, 99, 0) == _lib.MMR_EINVAL
+    assert lib.mmr_index_tune(eng._handle, _lib.TUNE_GEMM_VARIANT, 7) == _lib.MMR_EINVAL
+    with pytest.raises(KeyError):
+        eng.tune(variant="medium")
+
+
+def test_two_streams_one_handle_are_ordered_on_the_device():
+    """Two streams (and two host threads) searching through ONE handle with device outputs: the handle's
+    workspaces are shared, so the library orders the calls on the device (an event recorded at the end
+    of each call, waited on by the next call's stream) -- results must equal the serial ones."""
+    import threading
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(200_000, 128, seed=171))
+    eng = _engine(g, dtype="bfloat16", keep_host=False)
+    qs = [torch.from_numpy(osr.to_bf16_round(synth.make_embeddings(512, 128, seed=172 + i))).cuda() for i in range(2)]
+    want = [tuple(t.clone() for t in eng.search(q, 20)) for q in qs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [[None] * 6, [None] * 6]
+
+    def worker(i):
+        with torch.cuda.stream(streams[i]):
+            for it in range(6):
+                got[i][it] = eng.search(qs[i], 20)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    torch.cuda.synchronize()
+    for i in range(2):
+        for r, s_ in got[i]:
+            assert torch.equal(r, want[i][0]) and torch.equal(s_, want[i][1])
+
+
 def test_merged_engine_from_split_dumps(tmp_path):
     """Helpers.merged_engine: train + val dumps -> one HBM-resident gallery, rows and ids in the order
     createDumpEmbedding writes them (reference Helpers/dumpEmbedding.py:28-39)."""

@@ -200,3 +200,34 @@ def test_label_ranking_eval_matches_reference_golden():
     for key, val in want.items():
         assert abs(got[key] - val) < 1e-12, (key, got[key], val)
     assert table.shape == (z["embs"].shape[0], 4)
+
+
+def test_bruteforce_checker_is_pinned_on_the_numpy_oracle():
+    """oracle/bruteforce.py (torch, chunked -- the checker of the full-size GPU parity tests and of
+    bench.py's parity_check) returns what oracle.search.exact_topk returns, ties included."""
+    import torch
+    from oracle import search as osr
+    from oracle.bruteforce import bruteforce_topk, check_topk
+    rng = np.random.default_rng(5)
+    g = osr.to_bf16_round(rng.standard_normal((3000, 48)).astype(np.float32))
+    g[100:140] = g[7]
+    g[9] = 0.0
+    q = osr.to_bf16_round(rng.standard_normal((9, 48)).astype(np.float32))
+    q[2] = g[7]
+    q[4] = 0.0
+    for k in (1, 10, 100, 5000):
+        want_r, want_s = osr.exact_topk(q, g, k)
+        for chunk in (512, 1 << 19):
+            r, s = bruteforce_topk(torch.from_numpy(g), torch.from_numpy(q), k, chunk=chunk)
+            assert r.shape == want_r.shape
+            for i in range(9):
+                ok, why = osr.topk_matches(r[i], s[i], want_r[i], want_s[i], rtol=1e-6, atol=1e-7)
+                assert ok, (k, chunk, i, why)
+            # (BLAS does not return bit-equal dots for equal rows at different positions, so the order inside
+            # the 41-way tie is compared as a set by topk_matches, not position by position)
+            assert set(r[2][: min(k, 41)].tolist()) <= set(np.r_[7, 100:140].tolist())
+    r, s = bruteforce_topk(torch.from_numpy(g), torch.from_numpy(q), 10, row_offset=500)
+    ok, detail = check_topk(r, s, torch.from_numpy(g), torch.from_numpy(q), 10, row_offset=500)
+    assert ok, detail
+    bad = r.copy(); bad[0, 0] = 1234 + 500
+    assert not check_topk(bad, s, torch.from_numpy(g), torch.from_numpy(q), 10, row_offset=500)[0]
