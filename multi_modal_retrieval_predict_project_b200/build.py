@@ -43,7 +43,23 @@ def needs_build() -> bool:
     return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Default: libmmr_b200.so.  ``defines`` / ``out`` build a VARIANT library next to it for A/B runs and
+    diagnostics (e.g. ``defines=("MMR_DIAG",), out="libmmr_b200_diag.so"``; load it with MMR_B200_LIB=<path>):
+    its objects go to their own directory and it is always rebuilt when sources changed."""
+    global LIB, OBJ
+    if out is not None or defines:
+        tag = "_".join(d.replace("=", "") for d in defines) or "variant"
+        lib = os.path.join(HERE, out or f"libmmr_b200_{tag}.so")
+        saved = (LIB, OBJ)
+        LIB, OBJ = lib, os.path.join(CSRC, "_obj_" + tag)
+        extra = os.environ.get("NVCC_EXTRA", "")
+        os.environ["NVCC_EXTRA"] = (extra + " " + " ".join("-D" + d for d in defines)).strip()
+        try:
+            return build(force=force, verbose=verbose)
+        finally:
+            LIB, OBJ = saved
+            os.environ["NVCC_EXTRA"] = extra
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
@@ -82,4 +98,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m ...build [--force] [-v] [-DNAME[=VALUE] ...] [--out libname.so]
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    out_name = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=out_name))

@@ -58,10 +58,30 @@ constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KiB
 constexpr int kMaxSmemOptin = 232448;             // 227 KiB per CTA on sm_100
 constexpr int kEpiGroups = 2;                     // epilogue warpgroups (one per accumulator stage)
 constexpr int kEpiThreads = 128;                  // threads per epilogue warpgroup
-constexpr int kFirstEpiWarp = 4;
+// Warp roles.  The issue arbiter of an SM sub-partition prefers the HIGHEST eligible warp id, so the two
+// single-thread control warps (TMA producer, MMA issuer) sit ABOVE the eight epilogue warps they share their
+// sub-partitions with: a late TMA or MMA issue is a tensor-pipe bubble, a late epilogue instruction is not.
+// (MMR_CTRL_HIGH=0 restores the round-1 order -- control warps 0-3, epilogue 4-11 -- for A/B builds.)
+#ifndef MMR_CTRL_HIGH
+#define MMR_CTRL_HIGH 1
+#endif
+constexpr int kFirstEpiWarp = MMR_CTRL_HIGH ? 0 : 4;
+constexpr int kTmaWarp = MMR_CTRL_HIGH ? 8 : 0;
+constexpr int kMmaWarp = kTmaWarp + 1;
 constexpr int kNumThreads = 128 + kEpiGroups * kEpiThreads;  // 384
 constexpr int kRegsLow = 40, kRegsHigh = 232;     // 128*40 + 256*232 = 64512 <= 65536
 constexpr int kTrack = 8;                         // per-thread running top-8 used to publish pruning bounds
+// Epilogue split.  1: BOTH epilogue warpgroups drain EVERY accumulator tile, warpgroup g taking columns
+// [g * 128, g * 128 + 128) -- the tile's epilogue latency is halved.  With two TMEM stages the MMA of tile
+// t + 2 can only start when tile t has been drained, i.e. the drain has ONE MMA tile time, not two, whatever
+// the number of warpgroups that alternate on whole tiles (0: the round-1 scheme, kept for A/B builds:
+// warpgroup g drains tiles g, g + 2, ... on its own: 3.2-3.4 us per tile against 2.8 us for TMA + MMA alone).
+#ifndef MMR_EPI_SPLIT
+#define MMR_EPI_SPLIT 1
+#endif
+constexpr bool kSplit = MMR_EPI_SPLIT != 0;
+constexpr int kEpiCols = kSplit ? kBlockN / kEpiGroups : kBlockN;   // accumulator columns a warpgroup drains per tile
+constexpr int kEpiStep = kSplit ? 1 : kEpiGroups;                    // tile stride of a warpgroup
 
 struct __align__(16) SmemAux {
   float ginv[kAccStages][kBlockN];  // first: read as float4
@@ -367,18 +387,23 @@ __device__ __forceinline__ float warp_compact_dispatch(uint2* buf, int cnt, int 
 // (conservative) pre-threshold, append {t * inv_norm(q), col} at the cursor and advance it.
 // Everything after the compare is predicated -- no BSSY/BRA per score (a divergent branch per
 // score made the first version of this kernel epilogue-bound at 5x the MMA time).
-__device__ __forceinline__ void score_step(uint2*& ptr, float t, float tau_pre, float qinv, uint32_t col) {
+// The cursor is a 32-bit entry count: the only loop-carried dependency between consecutive scores is one
+// predicated 32-bit add (a predicated 64-bit pointer increment compiles to IADD3 + IMAD.X + two SELs per score,
+// a ~12-cycle chain link; the append path runs for about every second chunk of a short launch).
+__device__ __forceinline__ void score_step(uint2* buf, uint32_t& cnt, float t, float tau_pre, float qinv, uint32_t col) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       ".reg .f32 s;\n\t"
-      "setp.gt.f32 p, %1, %2;\n\t"
-      "@p mul.f32 s, %1, %3;\n\t"
-      "@p st.global.v2.b32 [%0], {s, %4};\n\t"
-      "@p add.u64 %0, %0, 8;\n\t"
+      ".reg .u64 a;\n\t"
+      "setp.gt.f32 p, %2, %3;\n\t"
+      "mad.wide.u32 a, %0, 8, %1;\n\t"
+      "@p mul.f32 s, %2, %4;\n\t"
+      "@p st.global.v2.b32 [a], {s, %5};\n\t"
+      "@p add.u32 %0, %0, 1;\n\t"
       "}"
-      : "+l"(ptr)
-      : "f"(t), "f"(tau_pre), "f"(qinv), "r"(col)
+      : "+r"(cnt)
+      : "l"(buf), "f"(t), "f"(tau_pre), "f"(qinv), "r"(col)
       : "memory");
 }
 
@@ -411,6 +436,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #ifndef MMR_DIAG
   debug_flags = 0;  // the diagnostic switches exist only in -DMMR_DIAG builds
 #endif
+#ifdef MMR_GEMM_TRACE  // slot 0: kernel entry of this CTA (low 48 bits) and its SM id (high 16 bits)
+  if (trace != nullptr && threadIdx.x == 0) {
+    unsigned long long now;
+    uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace[static_cast<size_t>(blockIdx.x) * 64] = (now & 0xFFFFFFFFFFFFull) | (static_cast<unsigned long long>(smid) << 48);
+  }
+#endif
   const int num_kc = d_pad / kBlockK;
   constexpr int kBStage = kPair ? kBBytes / 2 : kBBytes;  // gallery bytes this CTA stages per chunk
   constexpr int kStageBytes = kResident ? kBStage : kABytes + kBStage;
@@ -441,7 +475,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int tile_end = min(tile_begin + tiles_per_part, tiles_total);
   const int num_tiles = tile_end - tile_begin;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_g);
     for (int s = 0; s < num_stages; ++s) {
@@ -451,12 +485,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(&aux->q_full, 1);
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&aux->tmem_full[s], 1);
-      mbar_init(&aux->tmem_empty[s], kPair ? 2 : 1);  // one arrival per epilogue warpgroup of each CTA
+      // one arrival per epilogue warpgroup (that drains the stage) of each CTA
+      mbar_init(&aux->tmem_empty[s], (kPair ? 2 : 1) * (kSplit ? kEpiGroups : 1));
     }
     fence_barrier_init();
   }
   if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
-  if (warp == 1) {  // TMEM allocation (whole warp; in pair mode the same warp of both CTAs), address in smem
+  if (warp == kMmaWarp) {  // TMEM allocation (whole warp; in pair mode the same warp of both CTAs), address in smem
     if (kPair) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&aux->tmem_base)),
                    "r"(static_cast<uint32_t>(kTmemCols))
@@ -474,9 +509,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = aux->tmem_base;
 
-  if (warp < kFirstEpiWarp) {
+  if (warp >= kTmaWarp && warp < kTmaWarp + 4) {  // the control warpgroup (two of its warps only donate registers)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLow));
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
       // ===================== TMA producer =====================
       if (lane == 0) {
         // pair mode: both CTAs load into their own shared memory, but every byte is credited to the
@@ -555,7 +590,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         if (kProbe && progress != nullptr) *reinterpret_cast<volatile uint32_t*>(progress + unit) = 0xFFFFFFFFu;  // done
       }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
       // ===================== MMA issuer =====================
       if (lane == 0 && leader) {  // pair mode: only the leader CTA issues (for both SMs)
         constexpr uint32_t idesc = make_idesc(kPair ? 2 * kBlockM : kBlockM, kBlockN);
@@ -601,7 +636,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsHigh));
     // ===================== epilogue: scale + threshold + top-k =====================
-    const int group = (warp - kFirstEpiWarp) >> 2;  // == accumulator stage this warpgroup drains
+    const int group = (warp - kFirstEpiWarp) >> 2;  // split: the column half this warpgroup drains; else its TMEM stage
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;    // query row within the tile == TMEM lane
     const int q = m_tile * kBlockM + row_in_tile;
@@ -611,7 +646,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const bool q_ok = q < b;
     const float qinv = q_ok ? q_inv[q] : 0.f;
     uint2* const buf = cand + (static_cast<int64_t>(q_ok ? q : 0) * n_lists + list) * cap;
-    uint2* ptr = buf;                                // append cursor (count = ptr - buf)
+    uint32_t cnt = 0;                                // append cursor: entries in this thread's list
     float tau_local = q_ok ? -INFINITY : INFINITY;   // pre-threshold from this list's own k-th best (strict)
     float tau_pre = tau_local;                       // effective conservative threshold on acc * inv_norm(g)
     // running top-8 of the best-of-chunk final scores this thread has appended (a subset of its list,
@@ -627,38 +662,44 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const bool probe = kProbe && tau_pub != nullptr && pub_rank <= kTrack && (debug_flags & 2) == 0;  // warp-uniform
     const int epi_tid = threadIdx.x - (kFirstEpiWarp * 32 + group * kEpiThreads);  // 0..127
     const int64_t range_end = min(static_cast<int64_t>(tile_end) * kBlockN, n);
-    const uint32_t full_bytes = static_cast<uint32_t>(cap - 32) * 8u;
+    const uint32_t full_cnt = static_cast<uint32_t>(cap - 32);  // a chunk appends at most 32 entries
     const uint32_t nan_bits = 0x7FC00000u;           // marks gallery rows outside the range: never a hit
     const int bar_id = 1 + group;                    // named barrier of this warpgroup
     float* const ginv = aux->ginv[group];
     const uint32_t ginv_s = smem_u32(ginv);
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(group * kBlockN);
+    // TMEM address of this warp's lanes; the column offset of the stage / half is added per tile
+    const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int first_tile = kSplit ? 0 : group;       // first tile this warpgroup drains
+    const int col0 = kSplit ? group * kEpiCols : 0;  // first accumulator column this warpgroup drains
 
-    // inverse norms of this group's first tile; later tiles are prefetched one tile (of the group) ahead
+    // inverse norms of this group's columns of its first tile; later tiles are prefetched one (group) tile ahead
     float gnext0 = __uint_as_float(nan_bits), gnext1 = gnext0;
-    if (group < num_tiles) {
-      const int64_t r0 = static_cast<int64_t>(tile_begin + group) * kBlockN + epi_tid, r1 = r0 + kEpiThreads;
+    if (first_tile < num_tiles) {
+      const int64_t r0 = static_cast<int64_t>(tile_begin + first_tile) * kBlockN + col0 + epi_tid, r1 = r0 + kEpiThreads;
       if (r0 < range_end) gnext0 = __ldg(inv_norm + r0);
-      if (r1 < range_end) gnext1 = __ldg(inv_norm + r1);
+      if (!kSplit && r1 < range_end) gnext1 = __ldg(inv_norm + r1);
     }
 
-    for (int t = group; t < num_tiles; t += kEpiGroups) {
+    for (int t = first_tile; t < num_tiles; t += kEpiStep) {
+      const int acc = kSplit ? (t & 1) : group;      // accumulator stage of tile t
       const uint32_t acc_phase = (t >> 1) & 1u;
-      const int64_t n0 = static_cast<int64_t>(tile_begin + t) * kBlockN;
+      const uint32_t taddr = taddr_lane + static_cast<uint32_t>(acc * kBlockN + col0);
+      const int64_t n0 = static_cast<int64_t>(tile_begin + t) * kBlockN + col0;   // first gallery row of the columns drained
       ginv[epi_tid] = gnext0;
-      ginv[epi_tid + kEpiThreads] = gnext1;
+      if (!kSplit) ginv[epi_tid + kEpiThreads] = gnext1;
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // ginv of this tile is complete
       gnext0 = gnext1 = __uint_as_float(nan_bits);
-      if (t + kEpiGroups < num_tiles) {
-        const int64_t r0 = n0 + kEpiGroups * kBlockN + epi_tid, r1 = r0 + kEpiThreads;
+      if (t + kEpiStep < num_tiles) {
+        const int64_t r0 = n0 + kEpiStep * kBlockN + epi_tid, r1 = r0 + kEpiThreads;
         if (r0 < range_end) gnext0 = __ldg(inv_norm + r0);
-        if (r1 < range_end) gnext1 = __ldg(inv_norm + r1);
+        if (!kSplit && r1 < range_end) gnext1 = __ldg(inv_norm + r1);
       }
       // refresh the cross-CTA pruning bound (0 = "not published yet" => no pruning); purely
       // advisory and monotone, so stale reads are safe
       // (on every tile for the first `early_tiles` tiles of the group: right after start-up the bound
       // moves fastest and an early bound keeps the lists from filling with the first few hundred rows)
-      if (tau_pub != nullptr && t >= kEpiGroups && q_ok &&
+      // (split: warpgroup g refreshes on the tiles with t % 2 == g, the cadence of the unsplit scheme)
+      if (tau_pub != nullptr && t >= kEpiGroups && q_ok && (!kSplit || (t & 1) == group) && (debug_flags & 16) == 0 &&
           ((t >> 1) < early_tiles || ((t >> 1) % refresh_tiles) == 0)) {
         uint32_t g = 0xFFFFFFFFu;
         for (int p = 0; p < n_lists; ++p) {
@@ -667,7 +708,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         if (g != 0u) tau_pre = fmaxf(tau_local, pre_threshold(ordered_to_f32(g), qinv));
       }
-      mbar_wait(&aux->tmem_full[group], acc_phase);
+      mbar_wait(&aux->tmem_full[acc], acc_phase);
       tc_fence_after();
 #ifdef MMR_GEMM_TRACE  // diagnostic build only (scripts/trace_gemm.py): when did accumulator tile t become ready
       if (trace != nullptr && epi_tid == 0 && (t < 40 || (group == 0 && (t & 31) == 0 && (t >> 5) < 23))) {
@@ -687,28 +728,34 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // the REAL pass over the same tile and everything after it.  The maxima are not stored by the probe:
       // the tracker is reset, the real pass re-appends them (they are >= this list's bound >= g), so the
       // published claim "r entries >= bound in this list" holds from the end of the real pass on.
-      if (kProbe && t == group && probe && (debug_flags & 1) == 0) {
+      if (kProbe && t == first_tile && probe && (debug_flags & 1) == 0) {
 #pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
+        for (int c = 0; c < kEpiCols / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
-          float m = -INFINITY;
+          // maxima of the two 16-column halves of the chunk (split: a half tile has only 4 chunks of 32,
+          // and the published rank r = ceil(k / n_lists) needs up to kTrack = 8 distinct entries)
+          float mh[2] = {-INFINITY, -INFINITY};
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float g0, g1, g2, g3;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3)
                          : "r"(ginv_s + static_cast<uint32_t>((c * 32 + j4 * 4) * 4)));
-            m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) * g0, __uint_as_float(v[j4 * 4 + 1]) * g1),
-                               fmaxf(__uint_as_float(v[j4 * 4 + 2]) * g2, __uint_as_float(v[j4 * 4 + 3]) * g3)));
+            mh[j4 >> 2] = fmaxf(mh[j4 >> 2],
+                                fmaxf(fmaxf(__uint_as_float(v[j4 * 4 + 0]) * g0, __uint_as_float(v[j4 * 4 + 1]) * g1),
+                                      fmaxf(__uint_as_float(v[j4 * 4 + 2]) * g2, __uint_as_float(v[j4 * 4 + 3]) * g3)));
           }
-          float x = m * qinv;
 #pragma unroll
-          for (int i = 0; i < kTrack; ++i) {
-            const float hi = fmaxf(top[i], x);
-            x = fminf(top[i], x);
-            top[i] = hi;
+          for (int h = 0; h < (kSplit ? 2 : 1); ++h) {
+            float x = (kSplit ? mh[h] : fmaxf(mh[0], mh[1])) * qinv;
+#pragma unroll
+            for (int i = 0; i < kTrack; ++i) {
+              const float hi = fmaxf(top[i], x);
+              x = fminf(top[i], x);
+              top[i] = hi;
+            }
           }
         }
         if (track) {
@@ -737,10 +784,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
 #pragma unroll 1
-      for (int c = 0; c < ((debug_flags & 1) ? 0 : kBlockN / 32); ++c) {
+      for (int c = 0; c < ((debug_flags & 1) ? 0 : kEpiCols / 32); ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
+#ifdef MMR_DIAG
+        if (debug_flags & 4) {  // TMEM loads only: no scaling, no filter (results are garbage)
+          if ((v[0] ^ v[31]) == 0x7FFFFFFFu) cnt += 1;
+          continue;
+        }
+#endif
         // fast path: t_j = acc_j * inv_norm(g_j) and the chunk maximum (NaN = out-of-range column,
         // ignored by fmaxf); almost every chunk ends here once the threshold has tightened
         float tv[32];
@@ -759,20 +812,28 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           gm[j4] = fmaxf(fmaxf(tv[j4 * 4 + 0], tv[j4 * 4 + 1]), fmaxf(tv[j4 * 4 + 2], tv[j4 * 4 + 3]));
           m = fmaxf(m, gm[j4]);
         }
+#ifdef MMR_DIAG
+        if (debug_flags & 8) {  // scaling + maxima only: never take the append path (results are garbage)
+          if (m == 123.456f) cnt += 1;
+          continue;
+        }
+#endif
         if (__any_sync(0xffffffffu, m > tau_pre)) {  // warp-uniform
           const uint32_t colbase = static_cast<uint32_t>(n0) + static_cast<uint32_t>(c * 32);
           // second-level filter: only the groups of 4 columns in which some lane has a hit run the
           // predicated append (typically 1-3 of 8)
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            if (__any_sync(0xffffffffu, gm[j4] > tau_pre)) {
-              score_step(ptr, tv[j4 * 4 + 0], tau_pre, qinv, colbase + j4 * 4 + 0);
-              score_step(ptr, tv[j4 * 4 + 1], tau_pre, qinv, colbase + j4 * 4 + 1);
-              score_step(ptr, tv[j4 * 4 + 2], tau_pre, qinv, colbase + j4 * 4 + 2);
-              score_step(ptr, tv[j4 * 4 + 3], tau_pre, qinv, colbase + j4 * 4 + 3);
+            if (__any_sync(0xffffffffu, gm[j4] > tau_pre) && (debug_flags & 32) == 0) {
+              score_step(buf, cnt, tv[j4 * 4 + 0], tau_pre, qinv, colbase + j4 * 4 + 0);
+              score_step(buf, cnt, tv[j4 * 4 + 1], tau_pre, qinv, colbase + j4 * 4 + 1);
+              score_step(buf, cnt, tv[j4 * 4 + 2], tau_pre, qinv, colbase + j4 * 4 + 2);
+              score_step(buf, cnt, tv[j4 * 4 + 3], tau_pre, qinv, colbase + j4 * 4 + 3);
             }
           }
-          if (track && m > tau_pre) {  // m was appended above: fold it into the running top-8 and publish
+          // m was appended above: fold it into the running top-8 and publish.  The insertion only changes the
+          // array when x beats its last (smallest) slot -- the common case is a hit that does not
+          if (track && m > tau_pre && m * qinv > top[kTrack - 1] && (debug_flags & 64) == 0) {
             float x = m * qinv;
 #pragma unroll
             for (int i = 0; i < kTrack; ++i) {
@@ -787,20 +848,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           }
           // make room for the next 32 columns: compact every list of this warp that is nearly full
-          const uint32_t used =
-              static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ptr) - reinterpret_cast<uintptr_t>(buf));
-          uint32_t need = __ballot_sync(0xffffffffu, used > full_bytes);
+          uint32_t need = (debug_flags & 128) ? 0u : __ballot_sync(0xffffffffu, cnt > full_cnt);
           while (need != 0u) {
             const int src = __ffs(need) - 1;
             need &= need - 1u;
             uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
-            const int scnt = static_cast<int>(__shfl_sync(0xffffffffu, used, src) >> 3);
+            const int scnt = static_cast<int>(__shfl_sync(0xffffffffu, cnt, src));
             __syncwarp();
             float rth = 0.f;
             const float new_tau = warp_compact_dispatch(sbuf, scnt, k, pub_rank, cap, lane,
                                                         tau_pub != nullptr ? &rth : nullptr);
             if (lane == src) {
-              ptr = buf + k;
+              cnt = static_cast<uint32_t>(k);
               tau_local = pre_threshold(new_tau, qinv);
               tau_pre = fmaxf(tau_pre, tau_local);
               if (tau_pub != nullptr && rth > published) {
@@ -815,59 +874,76 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // all 4 warps are done with TMEM stage + ginv
       if (epi_tid == 0) {  // the MMA issuer (the leader CTA's in pair mode) may overwrite this stage
         if (kPair)
-          mbar_arrive_cluster(mapa_rank(smem_u32(&aux->tmem_empty[group]), 0u));
+          mbar_arrive_cluster(mapa_rank(smem_u32(&aux->tmem_empty[acc]), 0u));
         else
-          mbar_arrive_n(&aux->tmem_empty[group], 1);
+          mbar_arrive_n(&aux->tmem_empty[acc], 1);
       }
     }
+#ifdef MMR_GEMM_TRACE
+    if (trace != nullptr && epi_tid == 0 && group == 0) {  // slot 63: this CTA's last tile has been drained
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[static_cast<size_t>(blockIdx.x) * 64 + 63] = now;
+    }
+#endif
     // final pass per list so that select.cu merges lists of <= k entries: first drop everything below the
     // cross-list bound (one sweep, no selection; typically leaves 10-30 entries), and only if more than k
     // remain select the exact top-k
     {
-      int cnt = static_cast<int>(ptr - buf);
-      uint32_t gfin = 0u;  // ordered score; 0 = no bound
-      if (kProbe && tau_pub != nullptr && q_ok && cnt > k) {
-        gfin = 0xFFFFFFFFu;
+      int fcnt = static_cast<int>(cnt);
+      if (kProbe && tau_pub != nullptr && q_ok && fcnt > k) {
+        uint32_t gfin = 0xFFFFFFFFu;  // ordered score; 0 = no bound
         for (int p = 0; p < n_lists; ++p) {
           const uint32_t v = __ldcg(tau_pub + static_cast<int64_t>(p) * b_pad + q);
           gfin = v < gfin ? v : gfin;
         }
+        if (gfin != 0u) {
+          // Lane-private stable in-place filter of THIS thread's list (kept entries only move to lower
+          // indices).  Eight loads are in flight before anything is stored: the warp-cooperative version
+          // (one list at a time, a dependent L2 round trip per 32 entries) took 40-80 us per CTA for lists of
+          // 100-150 entries -- 2 x 80 us of a 4.2 ms launch at the N = 8 shard size.
+          // (16-byte loads through L1: two entries per request, a 128-byte line serves 16 -- 8-byte .cg loads
+          // fetched a 32-byte L2 sector per entry and made this sweep L2-bandwidth-bound)
+          int w = 0;
+          const uint4* buf2 = reinterpret_cast<const uint4*>(buf);   // lists are 16-byte aligned (cap is even)
+          for (int i0 = 0; i0 < fcnt; i0 += 16) {
+            uint4 e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = (i0 + 2 * j < fcnt) ? buf2[(i0 >> 1) + j] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (i0 + 2 * j < fcnt && f32_to_ordered(__uint_as_float(e[j].x)) >= gfin) buf[w++] = make_uint2(e[j].x, e[j].y);
+              if (i0 + 2 * j + 1 < fcnt && f32_to_ordered(__uint_as_float(e[j].z)) >= gfin) buf[w++] = make_uint2(e[j].z, e[j].w);
+            }
+          }
+          fcnt = w;
+        }
       }
-      uint32_t need = __ballot_sync(0xffffffffu, q_ok && cnt > k);
+      __syncwarp();
+      uint32_t need = __ballot_sync(0xffffffffu, q_ok && fcnt > k);   // rare: still more than k after the filter
       while (need != 0u) {
         const int src = __ffs(need) - 1;
         need &= need - 1u;
         uint2* sbuf = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(buf), src));
-        int scnt = __shfl_sync(0xffffffffu, cnt, src);
-        const uint32_t gsrc = __shfl_sync(0xffffffffu, gfin, src);
+        const int scnt = __shfl_sync(0xffffffffu, fcnt, src);
         __syncwarp();
-        if (kProbe && gsrc != 0u) {  // stable in-place filter: kept entries only move to lower indices
-          int base = 0;
-          for (int i0 = 0; i0 < scnt; i0 += 32) {
-            const int i = i0 + lane;
-            const uint2 e = (i < scnt) ? sbuf[i] : make_uint2(0u, 0u);
-            const bool keep = i < scnt && f32_to_ordered(__uint_as_float(e.x)) >= gsrc;
-            const uint32_t mk = __ballot_sync(0xffffffffu, keep);
-            __syncwarp();
-            if (keep) sbuf[base + __popc(mk & ((1u << lane) - 1u))] = e;
-            base += __popc(mk);
-            __syncwarp();
-          }
-          scnt = base;
-        }
-        if (scnt > k) {
-          (void)warp_compact_dispatch(sbuf, scnt, k, k, cap, lane, nullptr);
-          scnt = k;
-        }
-        if (lane == src) cnt = scnt;
+        (void)warp_compact_dispatch(sbuf, scnt, k, k, cap, lane, nullptr);
+        if (lane == src) fcnt = k;
       }
-      if (q_ok) counts[static_cast<int64_t>(q) * n_lists + list] = cnt;
+      if (q_ok) counts[static_cast<int64_t>(q) * n_lists + list] = fcnt;
     }
+#ifdef MMR_GEMM_TRACE
+    if (trace != nullptr && epi_tid == 0 && group == 0) {  // slot 62: final per-list pass done
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[static_cast<size_t>(blockIdx.x) * 64 + 62] = now;
+    }
+#endif
   }
 
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();  // pair: neither CTA leaves while the other may still touch it
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     if (kPair)
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),

@@ -296,7 +296,12 @@ class ShardedSearcher:
         for i, batch in enumerate(host_batches):
             slot = i & 1
             if qd[slot] is None or qd[slot].shape != batch.shape:
-                qd[slot] = torch.empty(batch.shape, dtype=torch.float32, device=dev)
+                # allocated FROM THE COPY STREAM's pool: a block of the compute stream's pool may still be
+                # read by kernels in flight (temporaries of the previous batch that Python has already
+                # released), and the copy stream does not wait for those
+                with torch.cuda.stream(s_in):
+                    qd[slot] = torch.empty(batch.shape, dtype=torch.float32, device=dev)
+                qd[slot].record_stream(s_cmp)
             if i >= 2:
                 s_in.wait_event(ev_cmp[slot])          # the search of batch i - 2 has consumed qd[slot]
             with torch.cuda.stream(s_in):
