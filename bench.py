@@ -626,6 +626,7 @@ def main():
             line["cpu_baseline"] = cpu_reference_run(args, 2, 1)
     elif not args.no_extra and args.cfg4_rows > 0:
         # ---------------- N >= 2: BASELINE configs[3] (100M x 512 row-sharded, batch 4096, top-100) -------
+        searcher.close()                                   # collective: unmap the peers, barrier, free
         del engine, searcher, reranker, masks, kg, gallery
         torch.cuda.empty_cache()
         line["cfg4"] = run_cfg4(args, dev, rank, world, local_rank, dist, peak_tf, gemm_roofline)

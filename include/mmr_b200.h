@@ -160,22 +160,29 @@ int mmr_apply_order(const int64_t* rows, const int32_t* order, const double* sco
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU exchange over NVLink peer memory (gallery row-sharded, one process per GPU; the
  * replacement for "concatenate every shard's candidates and argsort", i.e. the distributed form
- * of Evaluate/retrieval_overlap.py:85,90).  Queries are split across the ranks; the owner of a
- * query merges the G local top-K lists and reranks them.  No collective library call is on the
- * data path: lists and results move with peer stores issued by the kernels themselves.
- *   create    allocate this rank's region (sized for b_max queries, k_max results)
- *   handle    CUDA IPC handle of the region (mmr_exchange_handle_bytes() bytes) -- exchange the
- *             handles of all ranks out of band (torch.distributed all_gather) and pass them,
- *             rank-major, to open
- *   scatter   fused kernel: fp32 cosine of this rank's (b, k) local candidates (reranker.py:298)
- *             + stores of {score, cosine, global row} into the owners' regions + signal
- *   merge     wait for all ranks' lists of step `step`, merge this rank's query slice
- *             [rank*ceil(b/G), ...) -> (n_local, k) scores / rows / cosines, best first
- *   publish   store this rank's slice of the final (ids, combined scores) (n_local, keep) into
- *             every rank's result buffer + signal
- *   collect   wait for all slices; *ids / *fin point at the full (b, keep) result in this
- *             rank's region (valid until step + 2 is scattered)
- * `step` must increase by one per round on every rank (buffers alternate by its parity).
+ * of Evaluate/retrieval_overlap.py:85,90, followed by Reranker.rerank, Retrieval/reranker.py:240-333).
+ * Queries are split across the ranks; the owner of a query merges the G local top-K lists and reranks
+ * them.  No collective library call is on the data path: lists and results move with peer stores issued
+ * by the kernels on either side of the exchange.
+ *   create          allocate this rank's region (sized for b_max queries, k_max <= 128 results)
+ *   handle          CUDA IPC handle of the region (mmr_exchange_handle_bytes() bytes) -- exchange the
+ *                   handles of all ranks out of band (torch.distributed all_gather) and pass them,
+ *                   rank-major, to open
+ *   search_scatter  mmr_search whose selection kernel stores every query's top-k {score, global row}
+ *                   straight into the OWNER rank's region (owner of q = q / ceil(b / G)) + signal
+ *   rerank          ONE kernel per owner, one CTA per owned query: wait for all ranks' lists of `step`, merge,
+ *                   label / KG features + min-max + combine + order (the embedding feature, reranker.py:298,
+ *                   is the search score the candidate was found with; a candidate's record index is its
+ *                   GLOBAL row id; q_rec (b) device array of the queries' record indices), store the
+ *                   query's (ids, combined scores) (keep = topk or k) into EVERY rank's result buffer,
+ *                   signal; then wait for all ranks' slices.  *ids / *fin point at the full (b, keep) result
+ *                   in this rank's region (valid until step + 2 is scattered).
+ *   close_peers     unmap the peers' regions; put a barrier between this and destroy (which frees the
+ *                   region the peers had mapped)
+ * `step` must increase by one per round on every rank (buffers alternate by its parity), and all ranks
+ * must run a step with the same (b, k).  Every device-side wait is bounded (set_timeout, default 20 s) and
+ * gives up at once when a peer calls abort; a wait that gives up, or a (b, k) mismatch between ranks, makes
+ * the next call on the handle (and status) return MMR_ECUDA instead of hanging the GPU.
  * ------------------------------------------------------------------------------------- */
 typedef struct mmr_exchange mmr_exchange;
 int mmr_exchange_create(mmr_exchange** out, int32_t rank, int32_t world, int32_t b_max, int32_t k_max,
@@ -183,15 +190,17 @@ int mmr_exchange_create(mmr_exchange** out, int32_t rank, int32_t world, int32_t
 int mmr_exchange_handle_bytes(void);
 int mmr_exchange_handle(mmr_exchange* ex, void* handle_out);
 int mmr_exchange_open(mmr_exchange* ex, const void* handles);
+int mmr_exchange_set_timeout(mmr_exchange* ex, int32_t milliseconds);
+/* *code (may be NULL): 0 ok, 1 / 2 timed out waiting for lists / results, 3 (b, k) mismatch, 4 aborted */
+int mmr_exchange_status(mmr_exchange* ex, int32_t* code);
+int mmr_exchange_abort(mmr_exchange* ex);
+int mmr_exchange_close_peers(mmr_exchange* ex);
 int mmr_exchange_destroy(mmr_exchange* ex);
-int mmr_exchange_scatter(mmr_exchange* ex, const mmr_index* index, const float* q_emb, const int64_t* rows,
-                         const float* scores, int32_t b, int32_t k, uint32_t step, void* stream);
-int mmr_exchange_merge(mmr_exchange* ex, int32_t b, int32_t k, uint32_t step, float* out_scores,
-                       int64_t* out_rows, float* out_cos, void* stream);
-int mmr_exchange_publish(mmr_exchange* ex, const int64_t* ids, const double* fin, int32_t b, int32_t keep,
-                         uint32_t step, void* stream);
-int mmr_exchange_collect(mmr_exchange* ex, int32_t b, int32_t keep, uint32_t step, const int64_t** ids,
-                         const double** fin, void* stream);
+int mmr_search_scatter(mmr_index* index, mmr_exchange* ex, const void* q, int32_t b, int32_t q_dtype, int32_t k,
+                       int32_t algo, uint32_t step, void* stream);
+int mmr_exchange_rerank(mmr_exchange* ex, const mmr_rerank_tables* tables, const int64_t* q_rec, int32_t b,
+                        int32_t k, double alpha, double beta, double gamma, int32_t topk, uint32_t step,
+                        const int64_t** ids, const double** fin, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Rerank.  Replaces Reranker.rerank (Retrieval/reranker.py:240-333).
@@ -236,6 +245,18 @@ int mmr_rerank_with_cos(const mmr_rerank_tables* tables, const float* emb_cos, c
 int mmr_rerank_combine(const double* raw, const int32_t* cand_count, int32_t b, int32_t k, double alpha,
                        double beta, double gamma, int32_t topk, int32_t* out_order, double* out_scores,
                        int32_t device, void* stream);
+/* The fused tail of a search step (single shard): rerank the search result itself.  rows / scores (b, k) as
+ * written by mmr_search (k <= 128; -1 rows = padding); the embedding feature (reranker.py:298) is the search
+ * score, a candidate's record index is its GLOBAL row id, q_rec (b) the queries' record indices (-1 =
+ * unknown).  One kernel: label / KG features, min-max, combine, order.  Outputs what retrieve(...,
+ * reranker=...) returns (Retrieval/retrieval.py:257-269): out_ids / out_final (b, keep), keep = topk or k,
+ * ids in reranked order (-1 pad) + combined scores; out_scores4 (b, keep, 4), may be NULL, = final, emb_n,
+ * lab_n, kg_n of Reranker.rerank's tuples.  MMR_EUNSUP for k > 128 or a KG dimension the kernel does not
+ * cover (> 512 or not a multiple of 4): use mmr_rerank then. */
+int mmr_rerank_scored(const mmr_rerank_tables* tables, const int64_t* rows, const float* scores,
+                      const int64_t* q_rec, int32_t b, int32_t k, double alpha, double beta, double gamma,
+                      int32_t topk, int64_t* out_ids, double* out_final, double* out_scores4, int32_t device,
+                      void* stream);
 /* features + combine in one call (single-shard path). */
 int mmr_rerank(const mmr_index* index, const mmr_rerank_tables* tables, const float* q_emb,
                const float* cand_emb, const int64_t* cand_rows, const int64_t* q_rec,

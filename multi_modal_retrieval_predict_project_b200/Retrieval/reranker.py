@@ -156,6 +156,7 @@ class Reranker:
                 if vecs:
                     kg[i] = self._pool(np.stack(vecs, axis=0))
         self.rec_ids, self.rec2row, self.label_columns = rec_ids, rec2row, cols
+        self._d_kg = int(d_kg)
         self._masks_host, self._kg_host = np.ascontiguousarray(masks), np.ascontiguousarray(kg)
         import torch
         h = _lib.C.c_void_p()
@@ -194,6 +195,7 @@ class Reranker:
         self.rec_ids = list(rec_ids) if rec_ids is not None else None
         self.rec2row = {str(r): i for i, r in enumerate(self.rec_ids)} if rec_ids is not None else {}
         self.label_columns = [f"bit{i}" for i in range(64 * words)]
+        self._d_kg = int(kg_vecs.shape[1])
         h = _lib.C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.mmr_rerank_tables_create(
@@ -349,6 +351,38 @@ class Reranker:
                                                      self.gamma, int(topk), _lib.ptr(order), _lib.ptr(sc),
                                                      self.device, _lib.current_stream(self.device)))
         return order, sc
+
+    # the rerank's embedding feature on the batched device paths (ShardedSearcher.retrieve_reranked):
+    # "search_score" = the score the candidate was found with (the same cosine, reranker.py:298, without a second
+    # K x D gather); "recompute" = fp32 cosine of the query as passed against the stored row
+    emb_feature = "search_score"
+
+    def fused_tail_ok(self, k: int) -> bool:
+        """Shapes the fused tail kernel covers (csrc/rerank_tail.cuh): k <= 128, KG dimension a multiple of 4
+        and <= 512."""
+        d_kg = getattr(self, "_d_kg", None)
+        return 1 <= int(k) <= 128 and d_kg is not None and d_kg % 4 == 0 and d_kg <= 512
+
+    def rerank_scored_device(self, rows, scores, q_rec, topk: int = 0, out=None, want_scores4: bool = False):
+        """The fused tail of a search step (``mmr_rerank_scored``): rerank a search result ``(rows, scores)``
+        (B, K) CUDA tensors whose embedding feature is the search score and whose record index is the global row
+        id.  Returns ``(ids (B, keep) int64, combined scores (B, keep) fp64)`` (+ ``(B, keep, 4)`` score columns
+        with ``want_scores4``) -- what ``retrieve(..., reranker=...)`` returns for a batch."""
+        import torch
+        b, k = rows.shape
+        keep = topk if 0 < topk < k else k
+        if out is None:
+            ids = torch.empty((b, keep), dtype=torch.int64, device=rows.device)
+            fin = torch.empty((b, keep), dtype=torch.float64, device=rows.device)
+        else:
+            ids, fin = out
+        s4 = torch.empty((b, keep, 4), dtype=torch.float64, device=rows.device) if want_scores4 else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.mmr_rerank_scored(self._tables, _lib.ptr(rows), _lib.ptr(scores), _lib.ptr(q_rec), b, k,
+                                                   self.alpha, self.beta, self.gamma, int(topk), _lib.ptr(ids),
+                                                   _lib.ptr(fin), _lib.ptr(s4), self.device,
+                                                   _lib.current_stream(self.device)))
+        return (ids, fin, s4) if want_scores4 else (ids, fin)
 
     def combine_device(self, raw, topk: int = 0):
         import torch

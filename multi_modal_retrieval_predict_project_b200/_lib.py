@@ -54,10 +54,13 @@ SIGNATURES = {
     "mmr_exchange_handle": [_vp, _vp],
     "mmr_exchange_open": [_vp, _vp],
     "mmr_exchange_destroy": [_vp],
-    "mmr_exchange_scatter": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, C.c_uint32, _vp],
-    "mmr_exchange_merge": [_vp, _i32, _i32, C.c_uint32, _vp, _vp, _vp, _vp],
-    "mmr_exchange_publish": [_vp, _vp, _vp, _i32, _i32, C.c_uint32, _vp],
-    "mmr_exchange_collect": [_vp, _i32, _i32, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), _vp],
+    "mmr_exchange_set_timeout": [_vp, _i32],
+    "mmr_exchange_status": [_vp, C.POINTER(_i32)],
+    "mmr_exchange_abort": [_vp],
+    "mmr_exchange_close_peers": [_vp],
+    "mmr_search_scatter": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, C.c_uint32, _vp],
+    "mmr_exchange_rerank": [_vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _i32, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), _vp],
+    "mmr_rerank_scored": [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _i32, _vp],
     "mmr_candidate_cosine": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
     "mmr_rerank_with_cos": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _f64, _i32, _vp, _vp, _i32, _vp],
     "mmr_rerank_tables_create": [C.POINTER(_vp), _vp, _i32, _vp, _i32, _i64, _i32, _vp],

@@ -15,42 +15,6 @@
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
-struct mmr_index {
-  int device = 0;
-  int num_sms = 148;
-  int64_t n = 0;
-  int d = 0, d_pad = 0;
-  int dtype = MMR_BF16;
-  int64_t row_offset = 0;
-  void* emb = nullptr;
-  bool owns_emb = true;
-  float* inv_norm = nullptr;
-  // Re-entrancy: the grow-only workspaces below are one set per handle.  `mu` serialises the host side of
-  // a call; `last_done` (recorded at the end of every call on its stream) makes the NEXT call's stream
-  // wait for the previous call's kernels, so two threads / streams sharing one handle never overlap on
-  // the device either (calls with host outputs synchronise anyway).
-  std::mutex mu;
-  cudaEvent_t last_done = nullptr;
-  cudaStream_t last_stream = nullptr;
-  bool has_last = false;
-  mmr::GemmTune tune;
-  int last_algo = 0, last_variant = 0, last_pair = 0, last_parts = 0, last_tiles_per_part = 0;
-  mmr::DeviceBuf q_in, q_store, q_f32, q_inv, scratch, excl_in, excl_local, partial, counts, tau_pub, out_scores, out_rows;
-  // live kernel timing (mmr_index_profile)
-  bool profiling = false;
-  std::vector<cudaEvent_t> ev_start, ev_stop;
-  size_t ev_used = 0;
-};
-
-struct mmr_rerank_tables {
-  int device = 0;
-  int64_t n_rec = 0;
-  int label_words = 0;
-  int d_kg = 0;
-  uint64_t* masks = nullptr;
-  float* kg = nullptr;
-};
-
 namespace mmr {
 
 static thread_local std::string g_last_error;
@@ -138,8 +102,6 @@ int stage_in(const void* src, size_t bytes, DeviceBuf& buf, cudaStream_t stream,
   return MMR_OK;
 }
 
-namespace {
-
 // Device validation is cached per ordinal: cudaGetDeviceProperties costs milliseconds and the
 // handle-less entry points (merge, rerank, metrics) run once per query batch.
 int check_device(int device, int* num_sms) {
@@ -182,6 +144,8 @@ int check_device(int device, int* num_sms) {
   if (num_sms != nullptr) *num_sms = sms;
   return MMR_OK;
 }
+
+namespace {
 
 // Per-call temporaries for handle-less entry points (stream-ordered allocations).
 struct CallScope {
@@ -464,14 +428,21 @@ int mmr_index_get_rows(const mmr_index* ix, const int64_t* rows, int64_t m, floa
   return cs.finish();
 }
 
-int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t k, int32_t algo,
-               const int64_t* exclude_rows, float* out_scores, int64_t* out_rows, void* stream_v) {
+}  // extern "C"
+
+namespace mmr {
+// mmr_search proper.  `sink` != nullptr (mmr_search_scatter): the per-query lists go straight into the owner
+// ranks' exchange regions; out_scores / out_rows are then optional device staging buffers.
+int search_impl(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t k, int32_t algo,
+                const int64_t* exclude_rows, float* out_scores, int64_t* out_rows, const PeerSink* sink,
+                void* stream_v) {
   MMR_REQUIRE(ix != nullptr, "mmr_search: index is NULL");
   MMR_REQUIRE(b >= 0 && k >= 1, "mmr_search: need b >= 0 and k >= 1");
   MMR_REQUIRE(q_dtype == MMR_F32 || q_dtype == MMR_BF16, "mmr_search: bad q_dtype");
   MMR_REQUIRE(algo == MMR_ALGO_AUTO || algo == MMR_ALGO_SCAN || algo == MMR_ALGO_GEMM, "mmr_search: bad algo");
   if (b == 0) return MMR_OK;
-  MMR_REQUIRE(q != nullptr && out_scores != nullptr && out_rows != nullptr, "mmr_search: NULL argument");
+  MMR_REQUIRE(q != nullptr && (sink != nullptr || (out_scores != nullptr && out_rows != nullptr)),
+              "mmr_search: NULL argument");
   if (k > MMR_MAX_K) return fail(MMR_EUNSUP, "mmr_search: k > MMR_MAX_K (1024)");
   if (algo == MMR_ALGO_GEMM && ix->dtype != MMR_BF16)
     return fail(MMR_EUNSUP, "mmr_search: the tcgen05 GEMM path needs a bf16 index");
@@ -503,9 +474,17 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
   }
 
   // outputs
-  const bool host_scores = !is_device_ptr(out_scores), host_rows = !is_device_ptr(out_rows);
+  const bool host_scores = sink == nullptr && !is_device_ptr(out_scores);
+  const bool host_rows = sink == nullptr && !is_device_ptr(out_rows);
   float* d_scores = out_scores;
   int64_t* d_rows = out_rows;
+  if (sink != nullptr && (k > 128 || d_scores == nullptr || d_rows == nullptr)) {
+    // shapes outside the fused select + scatter kernel stage the dense lists in the handle's buffers
+    MMR_TRY(ix->out_scores.ensure(static_cast<size_t>(b) * k * sizeof(float)));
+    MMR_TRY(ix->out_rows.ensure(static_cast<size_t>(b) * k * sizeof(int64_t)));
+    d_scores = ix->out_scores.as<float>();
+    d_rows = ix->out_rows.as<int64_t>();
+  }
   if (host_scores) {
     MMR_TRY(ix->out_scores.ensure(static_cast<size_t>(b) * k * sizeof(float)));
     d_scores = ix->out_scores.as<float>();
@@ -554,7 +533,7 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
     if (ev1) MMR_CUDA_TRY(cudaEventRecord(ev1, stream));
     MMR_TRY(launch_select_var(ix->partial.as<uint64_t>(), ix->counts.as<int32_t>(), b, gp.n_lists, gp.cap, k_eff, k,
                               ix->row_offset, d_excl, g_share_tau ? ix->tau_pub.as<uint32_t>() : nullptr,
-                              gp.m_tiles * 128, d_scores, d_rows, stream));
+                              gp.m_tiles * 128, d_scores, d_rows, stream, sink));
   } else {
     const float* q_f32 = nullptr;
     if (ix->dtype == MMR_F32) {
@@ -578,7 +557,7 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
                         sp, ix->partial.as<uint64_t>(), stream));
     if (ev1) MMR_CUDA_TRY(cudaEventRecord(ev1, stream));
     MMR_TRY(launch_select_keys(ix->partial.as<uint64_t>(), b, static_cast<int64_t>(sp.n_parts) * sp.kp, k,
-                               ix->row_offset, d_scores, d_rows, stream));
+                               ix->row_offset, d_scores, d_rows, stream, sink));
   }
 
   if (host_scores)
@@ -589,6 +568,14 @@ int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t
                                  cudaMemcpyDeviceToHost, stream));
   if (host_scores || host_rows) MMR_CUDA_TRY(cudaStreamSynchronize(stream));
   return leave_call(ix, stream);
+}
+}  // namespace mmr
+
+extern "C" {
+
+int mmr_search(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t k, int32_t algo,
+               const int64_t* exclude_rows, float* out_scores, int64_t* out_rows, void* stream_v) {
+  return search_impl(ix, q, b, q_dtype, k, algo, exclude_rows, out_scores, out_rows, nullptr, stream_v);
 }
 
 int mmr_merge_topk_strided(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in,
@@ -805,6 +792,34 @@ int mmr_rerank(const mmr_index* ix, const mmr_rerank_tables* t, const float* q_e
   MMR_TRY(cs.out(out_order, static_cast<size_t>(b) * keep, &d_order));
   MMR_TRY(cs.out(out_scores, static_cast<size_t>(b) * keep * 4, &d_sc));
   MMR_TRY(launch_rerank_combine(d_raw, d_cc, b, k, alpha, beta, gamma, topk, d_order, d_sc, cs.stream));
+  return cs.finish();
+}
+
+int mmr_rerank_scored(const mmr_rerank_tables* t, const int64_t* rows, const float* scores, const int64_t* q_rec,
+                      int32_t b, int32_t k, double alpha, double beta, double gamma, int32_t topk, int64_t* out_ids,
+                      double* out_final, double* out_scores4, int32_t device, void* stream_v) {
+  MMR_REQUIRE(b >= 0 && k >= 0 && topk >= 0, "mmr_rerank_scored: bad sizes");
+  if (b == 0 || k == 0) return MMR_OK;
+  MMR_REQUIRE(rows && scores && out_ids && out_final, "mmr_rerank_scored: NULL argument");
+  if (t != nullptr) device = t->device;
+  MMR_TRY(check_device(device, nullptr));
+  DeviceGuard guard(device);
+  CallScope cs(static_cast<cudaStream_t>(stream_v));
+  const int keep = (topk > 0 && topk < k) ? topk : k;
+  const size_t bk = static_cast<size_t>(b) * k, bo = static_cast<size_t>(b) * keep;
+  const int64_t *d_rows, *d_qr;
+  const float* d_sc;
+  int64_t* d_ids;
+  double *d_fin, *d_s4;
+  MMR_TRY(cs.in(rows, bk, &d_rows));
+  MMR_TRY(cs.in(scores, bk, &d_sc));
+  MMR_TRY(cs.in(q_rec, static_cast<size_t>(b), &d_qr));
+  MMR_TRY(cs.out(out_ids, bo, &d_ids));
+  MMR_TRY(cs.out(out_final, bo, &d_fin));
+  MMR_TRY(cs.out(out_scores4, bo * 4, &d_s4));
+  MMR_TRY(launch_rerank_scored(d_rows, d_sc, d_qr, t ? t->masks : nullptr, t ? t->label_words : 0, t ? t->kg : nullptr,
+                               t ? t->d_kg : 0, t ? t->n_rec : 0, b, k, alpha, beta, gamma, topk, d_ids, d_fin, d_s4,
+                               cs.stream));
   return cs.finish();
 }
 

@@ -1,244 +1,295 @@
 // Multi-GPU exchange over NVLink peer memory (one process per GPU, gallery row-sharded).
 //
-// The sharded search has one exchange step: every rank holds a local top-K
-// per query and the global top-K is the merge of the G local lists.  Instead of an NCCL all-gather
-// followed by a merge that every rank repeats for every query, the query batch is split across the
-// ranks ("owner" of query q = q / ceil(b / G)) and the exchange is fused into the kernels:
+// The sharded search has one exchange step: every rank holds a local top-K per query
+// and the global top-K is the merge of the G local lists.  Instead of an NCCL all-gather followed by a merge
+// and a rerank that every rank repeats for every query, the query batch is split across the ranks ("owner" of
+// query q = q / ceil(b / G)) and the exchange is the epilogue / prologue of the kernels on either side of it:
 //
-//   scatter   ONE kernel per rank computes the fp32 embedding cosine of its K local candidates
-//             (the rerank feature of Retrieval/reranker.py:298, evaluated by the rank that owns
-//             the gallery row) and stores {score, cosine, global row} for query q straight into
-//             the OWNER's exchange buffer with 128-bit NVLink stores -- the all-to-all is the
-//             kernel's epilogue.  A one-warp signal kernel then raises this rank's flag on every peer.
-//   merge     the owner waits for the G flags (a spinning one-warp kernel, stream-ordered), merges
-//             its slice of the queries out of the exchange buffer and reranks it.
-//   publish   the owner stores its slice of the final (ids, scores) into every rank's result buffer
-//             (peer stores again) and signals; collect waits for the G result flags.
+//   scatter   mmr_search_scatter: the search's selection kernel (select.cu, RemoteSink) stores every query's
+//             top-K {score, global row} straight into the OWNER's region with NVLink stores -- the all-to-all
+//             is that kernel's output -- and a one-warp kernel raises this rank's flag on every peer.
+//   rerank    mmr_exchange_rerank: ONE kernel per owner, one CTA per owned query: wait for the G flags
+//             (bounded spin), merge the G lists, label / KG features, min-max, combine, order
+//             (rerank_tail.cuh = Reranker.rerank, reference Retrieval/reranker.py:298-329), store the query's
+//             final (ids, scores) into EVERY rank's result buffer; the last CTA raises the result flags.
+//   collect   a one-warp kernel waits for the G result flags; the full (b, keep) result then sits in this
+//             rank's region.
 //
-// Buffers are double buffered by step parity: a rank can only start step s + 2 after it has seen
-// every peer's step s + 1 signal, which each peer raises (in stream order) after it finished
-// reading step s.  Peer mappings come from CUDA IPC handles exchanged once through
-// torch.distributed (plumbing); no NCCL call is on the data path.
+// Regions are double buffered by step parity: a rank can only start step s + 2 after it has seen every peer's
+// step s + 1 result flag, which each peer raises (in stream order) after it finished reading step s.  Peer
+// mappings come from CUDA IPC handles exchanged once through torch.distributed (plumbing); no collective
+// library call is on the data path.
+//
+// Failure handling: every wait is bounded (mmr_exchange_set_timeout, default 20 s) and checks an abort word
+// that mmr_exchange_abort raises on all peers; a wait that gives up -- or finds that a peer ran the step
+// with a different (b, k) -- writes a code into a host-mapped error word, which the next call on the handle
+// (and mmr_exchange_status) reports as MMR_ECUDA instead of hanging the GPU.
 #include <algorithm>
 #include <cstring>
 #include <vector>
 
 #include "internal.h"
+#include "rerank_tail.cuh"
+
+using mmr::kMaxWorld;
+using mmr::PeerSink;
+using mmr::PeerTable;
 
 namespace mmr {
-constexpr int kMaxWorld = 16;
-struct PeerTable {  // base address of every rank's region as mapped into THIS process
-  uint8_t* base[kMaxWorld];
+// control block at ctl_off of every region
+struct Ctl {
+  uint32_t list_flag[kMaxWorld];  // step of the last list block received from rank r
+  uint32_t res_flag[kMaxWorld];   // step of the last result slice received from rank r
+  uint32_t meta[kMaxWorld];       // (b, k) fingerprint rank r ran that step with
+  uint32_t abort;                 // != 0: give up waiting
+  uint32_t done[2];               // per parity: CTAs of the rerank kernel that have published
 };
+enum : uint32_t { kErrNone = 0, kErrTimeoutLists = 1, kErrTimeoutResults = 2, kErrMismatch = 3, kErrAborted = 4 };
 }  // namespace mmr
-using mmr::kMaxWorld;
-using mmr::PeerTable;
+using mmr::Ctl;
 
 struct mmr_exchange {
   int device = 0;
   int rank = 0, world = 1;
   int b_max = 0, k_max = 0;
-  size_t blob_bytes = 0;    // per parity: world * per_max * kp_max * 16
-  size_t result_bytes = 0;  // per parity: world * per_max * k_max * 16
-  size_t flags_off = 0, region_bytes = 0;
+  size_t list_bytes = 0;    // per parity: scores + rows, world * per_max * kp_max entries each
+  size_t result_bytes = 0;  // per parity: ids + scores, world * per_max * k_max entries each
+  size_t ctl_off = 0, region_bytes = 0;
   uint8_t* local = nullptr;
   PeerTable peers{};
   std::vector<void*> opened;
   bool open = false;
+  uint32_t* err_host = nullptr;  // host-mapped error word (written by a kernel that gives up)
+  uint32_t* err_dev = nullptr;
+  uint32_t timeout_ms = 20000;
 };
 
 namespace mmr {
 namespace {
 
-__device__ __forceinline__ float xbf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float xbf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
-
-// flags: uint32 [2 kinds][world]; kind 0 = blob of step arrived from src, kind 1 = result arrived from src
-__global__ void exchange_signal_kernel(PeerTable peers, size_t flags_off, int kind, int world, int my_rank,
-                                       uint32_t step) {
-  const int r = threadIdx.x;
-  if (r < world) {
-    __threadfence_system();  // everything this stream wrote to the peers before this kernel is ordered first
-    uint32_t* flag = reinterpret_cast<uint32_t*>(peers.base[r] + flags_off) + kind * world + my_rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(step) : "memory");
-  }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
-__global__ void exchange_wait_kernel(const uint32_t* __restrict__ flags, int world, uint32_t step) {
-  const int r = threadIdx.x;
+// Lanes r < world of ONE warp wait until flags[r] >= step (wrap-safe), at most timeout_ns, giving up at once
+// when the abort word is raised.  With `meta` the fingerprint every source rank published must equal `mine`.
+// On failure the code goes to the host-mapped error word.  Returns true (warp-uniform) when everything arrived.
+__device__ __forceinline__ bool wait_flags(const uint32_t* flags, const uint32_t* meta, uint32_t mine,
+                                           const uint32_t* abort_word, int world, uint32_t step, uint64_t timeout_ns,
+                                           uint32_t* err, uint32_t timeout_code) {
+  const int r = threadIdx.x & 31;
+  uint32_t code = kErrNone;
   if (r < world) {
-    uint32_t v;
+    const uint64_t t0 = global_ns();
     for (;;) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-      if (static_cast<int32_t>(v - step) >= 0) break;  // flags only grow (wrap-safe compare)
+      if (static_cast<int32_t>(ld_acquire_sys(flags + r) - step) >= 0) break;  // flags only grow
+      if (*reinterpret_cast<const volatile uint32_t*>(abort_word) != 0u) {
+        code = kErrAborted;
+        break;
+      }
+      if (global_ns() - t0 > timeout_ns) {
+        code = timeout_code;
+        break;
+      }
       __nanosleep(200);
     }
+    if (code == kErrNone && meta != nullptr && *reinterpret_cast<const volatile uint32_t*>(meta + r) != mine)
+      code = kErrMismatch;
+    if (code != kErrNone) {
+      *reinterpret_cast<volatile uint32_t*>(err) = code;
+      __threadfence_system();
+    }
   }
+  return __all_sync(0xffffffffu, code == kErrNone);
+}
+
+inline uint32_t fingerprint(int b, int k) {  // host: the (b, k) a rank ran a step with
+  return (static_cast<uint32_t>(b) * 2654435761u) ^ (static_cast<uint32_t>(k) * 40503u) ^ 0x9E3779B9u;
+}
+
+// kind 0: "my lists of `step` are in your region" (+ the (b, k) fingerprint), kind 1: "my result slice is"
+__global__ void exchange_signal_kernel(PeerTable peers, size_t ctl_off, int kind, int world, int my_rank, uint32_t step,
+                                       uint32_t meta) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    __threadfence_system();  // everything this stream stored into the peers before this kernel is ordered first
+    Ctl* ctl = reinterpret_cast<Ctl*>(peers.base[r] + ctl_off);
+    if (kind == 0) {
+      *reinterpret_cast<volatile uint32_t*>(&ctl->meta[my_rank]) = meta;
+      st_release_sys(&ctl->list_flag[my_rank], step);
+    } else {
+      st_release_sys(&ctl->res_flag[my_rank], step);
+    }
+  }
+}
+
+__global__ void exchange_wait_kernel(const Ctl* ctl, int kind, int world, uint32_t step, uint64_t timeout_ns,
+                                     uint32_t* err) {
+  (void)wait_flags(kind == 0 ? ctl->list_flag : ctl->res_flag, nullptr, 0u, &ctl->abort, world, step, timeout_ns, err,
+                   kind == 0 ? kErrTimeoutLists : kErrTimeoutResults);
   __threadfence_system();
 }
 
-// One CTA per query.  cosine(q, gallery row) of the K local candidates (fp32, safe_cos formula
-// dot / (||a|| * ||b||), 128-bit gathers, two candidates per warp in flight), staged in shared
-// memory, then the query's {scores, cosines, rows} lists go to the owner rank's buffer.
-template <int kIts>
-__global__ void __launch_bounds__(256)
-exchange_cos_scatter_kernel(const __nv_bfloat16* __restrict__ emb, int64_t n, int d_pad, int64_t row_offset,
-                            const float* __restrict__ q_emb, int d, const int64_t* __restrict__ rows,
-                            const float* __restrict__ scores, int k, int kp, int per, int my_rank, PeerTable peers,
-                            size_t off_scores, size_t off_cos, size_t off_rows) {
-  __shared__ __align__(16) float qs[kIts * 256];
-  __shared__ __align__(16) float s_cos[MMR_MAX_K];
-  const int q = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int nv = d_pad >> 3;
-  for (int i = threadIdx.x; i < kIts * 256; i += blockDim.x) qs[i] = i < d ? q_emb[static_cast<int64_t>(q) * d + i] : 0.f;
-  __syncthreads();
-  float qss = 0.f;
-#pragma unroll
-  for (int it = 0; it < kIts; ++it) {
-    const float4 a = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8);
-    const float4 c = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8 + 4);
-    qss = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, qss))));
-    qss = fmaf(c.x, c.x, fmaf(c.y, c.y, fmaf(c.z, c.z, fmaf(c.w, c.w, qss))));
-  }
-  qss = warp_sum(qss);
-  const int64_t base = static_cast<int64_t>(q) * k;
-  for (int j0 = warp * 2; j0 < k; j0 += nwarps * 2) {
-    uint4 x[2][kIts];
-    bool have[2];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int j = j0 + c;
-      int64_t local = j < k ? rows[base + j] - row_offset : -1;
-      have[c] = j < k && local >= 0 && local < n;
-      const uint4* ce = reinterpret_cast<const uint4*>(emb + (have[c] ? local : 0) * d_pad);
-#pragma unroll
-      for (int it = 0; it < kIts; ++it) {
-        const int u = it * 32 + lane;
-        x[c][it] = (have[c] && u < nv) ? __ldg(ce + u) : make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-    float dot[2] = {0.f, 0.f}, css[2] = {0.f, 0.f};
-#pragma unroll
-    for (int it = 0; it < kIts; ++it) {
-      const float4 qa = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8);
-      const float4 qb = *reinterpret_cast<const float4*>(qs + (it * 32 + lane) * 8 + 4);
-      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t w[4] = {x[c][it].x, x[c][it].y, x[c][it].z, x[c][it].w};
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float lo = xbf16_lo(w[h]), hi = xbf16_hi(w[h]);
-          dot[c] = fmaf(lo, qv[2 * h], dot[c]);
-          css[c] = fmaf(lo, lo, css[c]);
-          dot[c] = fmaf(hi, qv[2 * h + 1], dot[c]);
-          css[c] = fmaf(hi, hi, css[c]);
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        dot[c] += __shfl_xor_sync(0xffffffffu, dot[c], o);
-        css[c] += __shfl_xor_sync(0xffffffffu, css[c], o);
-      }
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (j0 + c < k) {
-          const float na = sqrtf(qss), nb = sqrtf(css[c]);
-          s_cos[j0 + c] = (have[c] && na != 0.f && nb != 0.f) ? dot[c] / (na * nb) : 0.f;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---- the exchange: this query's lists -> the owner rank's buffer (16-byte NVLink stores) ----
-  const int dest = q / per;
-  const int64_t slot = (static_cast<int64_t>(my_rank) * per + (q - dest * per)) * kp;  // element offset
-  uint8_t* const dbase = peers.base[dest];
-  float4* const d_sc = reinterpret_cast<float4*>(dbase + off_scores + slot * 4);
-  float4* const d_co = reinterpret_cast<float4*>(dbase + off_cos + slot * 4);
-  longlong2* const d_ro = reinterpret_cast<longlong2*>(dbase + off_rows + slot * 8);
-  for (int v = threadIdx.x; v < kp / 4; v += blockDim.x) {
-    float sc[4], co[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = v * 4 + e;
-      sc[e] = j < k ? scores[base + j] : -INFINITY;
-      co[e] = j < k ? s_cos[j] : 0.f;
-    }
-    d_sc[v] = make_float4(sc[0], sc[1], sc[2], sc[3]);
-    d_co[v] = make_float4(co[0], co[1], co[2], co[3]);
-  }
-  for (int v = threadIdx.x; v < kp / 2; v += blockDim.x) {
-    const int j = v * 2;
-    d_ro[v] = make_longlong2(j < k ? rows[base + j] : -1, j + 1 < k ? rows[base + j + 1] : -1);
-  }
-  __threadfence_system();
-}
+// One CTA per OWNED query: wait -> merge G lists -> rerank tail -> publish to every rank -> (last CTA) signal.
+struct RerankArgs {
+  const float* l_scores;   // this rank's list block of the step's parity: [world][per][kp]
+  const int64_t* l_rows;
+  Ctl* ctl;                // this rank's control block
+  TailTables t;
+  const int64_t* q_rec;    // (b) record index of every query of the batch
+  int q_lo, nloc, b, k, kp, per, world, my_rank, keep;
+  double alpha, beta, gamma;
+  PeerTable peers;
+  size_t off_ids, off_fin, ctl_off;
+  uint32_t step, meta;
+  uint64_t timeout_ns;
+  uint32_t* err;
+};
 
-// my slice of the final (ids, combined scores) -> every rank's result buffer
-__global__ void exchange_publish_kernel(const int64_t* __restrict__ ids, const double* __restrict__ fin, int64_t count,
-                                        int64_t dst_elem_off, int world, PeerTable peers, size_t off_ids,
-                                        size_t off_fin) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < count) {
-    const int64_t id = ids[i];
-    const double f = fin[i];
-    for (int r = 0; r < world; ++r) {
-      reinterpret_cast<int64_t*>(peers.base[r] + off_ids)[dst_elem_off + i] = id;
-      reinterpret_cast<double*>(peers.base[r] + off_fin)[dst_elem_off + i] = f;
+template <int kKIts>
+__global__ void __launch_bounds__(kTailThreads)
+exchange_rerank_kernel(RerankArgs a) {
+  __shared__ TailSmem sm;
+  __shared__ __align__(16) uint64_t keys[kMaxWorld * kTailMaxK];
+  __shared__ uint32_t s_bound;
+  __shared__ int s_m, s_ok, s_last;
+  const int tid = threadIdx.x;
+  const int ql = blockIdx.x;          // query within this rank's slice
+  const int q = a.q_lo + ql;          // query within the batch
+  if (tid == 0) {
+    s_bound = 0u;
+    s_m = 0;
+  }
+  if (tid < 32) {
+    const bool ok = wait_flags(a.ctl->list_flag, a.ctl->meta, a.meta, &a.ctl->abort, a.world, a.step, a.timeout_ns,
+                               a.err, kErrTimeoutLists);
+    if (tid == 0) s_ok = ok ? 1 : 0;
+  }
+  __syncthreads();
+  int count = 0;
+  if (s_ok) {
+    // ---- merge: a list whose k-th entry exists holds k candidates >= that entry, so nothing below the best such
+    // entry can be in the global top-k; the survivors are ranked by counting (keys are unique) ----
+    if (tid < a.world) {
+      const int64_t at = (static_cast<int64_t>(tid) * a.per + ql) * a.kp + (a.k - 1);
+      if (a.l_rows[at] >= 0) atomicMax(&s_bound, f32_to_ordered(a.l_scores[at]));
+    }
+    __syncthreads();
+    const uint32_t bound = s_bound;
+    const int total = a.world * a.kp;
+    for (int i = tid; i < total; i += kTailThreads) {
+      const int l = i / a.kp, j = i - l * a.kp;
+      const int64_t at = (static_cast<int64_t>(l) * a.per + ql) * a.kp + j;
+      const int64_t row = a.l_rows[at];
+      if (row >= 0) {
+        const uint64_t key = make_key(a.l_scores[at], static_cast<uint32_t>(row));
+        if (static_cast<uint32_t>(key >> 32) >= bound) keys[atomicAdd(&s_m, 1)] = key;
+      }
+    }
+    __syncthreads();
+    const int m = s_m;
+    for (int i = tid; i < m; i += kTailThreads) {
+      const uint64_t mine = keys[i];
+      int r = 0;
+      for (int j = 0; j < m; ++j) r += keys[j] > mine ? 1 : 0;
+      if (r < a.k) {
+        sm.cand_row[r] = static_cast<int64_t>(key_row(mine));
+        sm.cand_score[r] = key_score(mine);
+      }
+    }
+    count = m < a.k ? m : a.k;
+    __syncthreads();
+  }
+  // ---- rerank + publish: the query's final (ids, scores) go to every rank's result buffer ----
+  const int64_t base = static_cast<int64_t>(q) * a.keep;
+  rerank_tail<kKIts>(sm, count, a.q_rec[q], a.t, a.alpha, a.beta, a.gamma, a.keep,
+                     [&](int rank, int j, double fin, double, double, double) {
+                       const int64_t id = sm.cand_row[j];
+                       for (int r = 0; r < a.world; ++r) {
+                         reinterpret_cast<int64_t*>(a.peers.base[r] + a.off_ids)[base + rank] = id;
+                         reinterpret_cast<double*>(a.peers.base[r] + a.off_fin)[base + rank] = fin;
+                       }
+                     });
+  for (int rank = count + tid; rank < a.keep; rank += kTailThreads) {  // fewer candidates than `keep` (or a failed wait)
+    for (int r = 0; r < a.world; ++r) {
+      reinterpret_cast<int64_t*>(a.peers.base[r] + a.off_ids)[base + rank] = -1;
+      reinterpret_cast<double*>(a.peers.base[r] + a.off_fin)[base + rank] = 0.0;
     }
   }
+  // ---- the last CTA of the launch raises this rank's result flag on every peer ----
   __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(&a.ctl->done[a.step & 1u], 1u);
+    s_last = prev + 1u == gridDim.x ? 1 : 0;
+    if (s_last) a.ctl->done[a.step & 1u] = 0u;  // ready for step + 2
+  }
+  __syncthreads();
+  if (s_last && tid < a.world) {
+    __threadfence_system();
+    st_release_sys(&reinterpret_cast<Ctl*>(a.peers.base[tid] + a.ctl_off)->res_flag[a.my_rank], a.step);
+  }
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Layout {
+  int per, kp;
+  size_t off_scores, off_rows;  // lists, for the step's parity
+  size_t off_ids, off_fin;      // results, for the step's parity
+};
+Layout layout_for(const mmr_exchange* ex, int b, int k, int keep, uint32_t step) {
+  Layout L;
+  L.per = (b + ex->world - 1) / ex->world;
+  L.kp = (k + 3) / 4 * 4;
+  const size_t parity = step & 1u;
+  const size_t lists = static_cast<size_t>(ex->world) * L.per * L.kp;
+  L.off_scores = parity * ex->list_bytes;
+  L.off_rows = L.off_scores + align_up(lists * 4, 256);
+  L.off_ids = 2 * ex->list_bytes + parity * ex->result_bytes;
+  L.off_fin = L.off_ids + align_up(static_cast<size_t>(ex->world) * L.per * keep * 8, 256);
+  return L;
+}
+
+int check_call(mmr_exchange* ex, int b, int k, const char* who) {
+  if (ex == nullptr || !ex->open) return fail(MMR_EINVAL, std::string(who) + ": exchange is not open");
+  if (b < 1 || k < 1 || b > ex->b_max || k > ex->k_max)
+    return fail(MMR_EINVAL, std::string(who) + ": batch / k exceed the sizes the exchange was created for");
+  const uint32_t code = *reinterpret_cast<volatile uint32_t*>(ex->err_host);
+  if (code != kErrNone) {
+    static const char* what[] = {"", "timed out waiting for a peer's candidate lists", "timed out waiting for a peer's results",
+                                 "a peer ran the step with a different batch size or k", "aborted"};
+    return fail(MMR_ECUDA, std::string(who) + ": the exchange failed in an earlier step (" + what[code < 5 ? code : 0] +
+                               "); destroy it and create a new one");
+  }
+  return MMR_OK;
+}
 
 }  // namespace
 }  // namespace mmr
 
 using namespace mmr;
 
-namespace {
-struct Layout {
-  int per, kp;
-  size_t off_scores, off_cos, off_rows;  // within the region, for the given parity
-  size_t off_ids, off_fin;
-};
-Layout layout_for(const mmr_exchange* ex, int b, int k, uint32_t step) {
-  Layout L;
-  L.per = (b + ex->world - 1) / ex->world;
-  L.kp = (k + 3) / 4 * 4;
-  const size_t parity = step & 1u;
-  const size_t lists = static_cast<size_t>(ex->world) * L.per * L.kp;
-  const size_t blob0 = parity * ex->blob_bytes;
-  L.off_scores = blob0;
-  L.off_cos = blob0 + align_up(lists * 4, 256);
-  L.off_rows = L.off_cos + align_up(lists * 4, 256);
-  const size_t res0 = 2 * ex->blob_bytes + parity * ex->result_bytes;
-  L.off_ids = res0;
-  L.off_fin = res0 + align_up(static_cast<size_t>(ex->world) * L.per * k * 8, 256);
-  return L;
-}
-int check_sizes(const mmr_exchange* ex, int b, int k, const char* who) {
-  if (ex == nullptr || !ex->open) return fail(MMR_EINVAL, std::string(who) + ": exchange is not open");
-  if (b < 1 || k < 1 || b > ex->b_max || k > ex->k_max)
-    return fail(MMR_EINVAL, std::string(who) + ": batch / k exceed the sizes the exchange was created for");
-  return MMR_OK;
-}
-}  // namespace
-
 extern "C" {
 
 int mmr_exchange_create(mmr_exchange** out, int32_t rank, int32_t world, int32_t b_max, int32_t k_max, int32_t device) {
   MMR_REQUIRE(out != nullptr, "mmr_exchange_create: out is NULL");
+  *out = nullptr;
   MMR_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "mmr_exchange_create: bad rank / world");
-  MMR_REQUIRE(b_max >= 1 && k_max >= 1 && k_max <= MMR_MAX_K, "mmr_exchange_create: bad sizes");
+  MMR_REQUIRE(b_max >= 1 && k_max >= 1, "mmr_exchange_create: bad sizes");
+  if (k_max > kTailMaxK)
+    return fail(MMR_EUNSUP, "mmr_exchange_create: the fused exchange covers k <= 128 (use the all-gather transport)");
+  MMR_TRY(check_device(device, nullptr));
   DeviceGuard guard(device);
   if (!guard.ok) return fail(MMR_ENODEV, "mmr_exchange_create: cannot select the device (no CPU fallback)");
   mmr_exchange* ex = new mmr_exchange();
@@ -249,23 +300,27 @@ int mmr_exchange_create(mmr_exchange** out, int32_t rank, int32_t world, int32_t
   ex->k_max = k_max;
   const size_t per = (static_cast<size_t>(b_max) + world - 1) / world;
   const size_t kp = (static_cast<size_t>(k_max) + 3) / 4 * 4;
-  ex->blob_bytes = align_up(3 * 256 + static_cast<size_t>(world) * per * kp * 16, 256);
+  ex->list_bytes = align_up(2 * 256 + static_cast<size_t>(world) * per * kp * 12, 256);
   ex->result_bytes = align_up(2 * 256 + static_cast<size_t>(world) * per * k_max * 16, 256);
-  ex->flags_off = 2 * ex->blob_bytes + 2 * ex->result_bytes;
-  ex->region_bytes = ex->flags_off + 256;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->local), ex->region_bytes);
-  if (e != cudaSuccess) {
+  ex->ctl_off = 2 * ex->list_bytes + 2 * ex->result_bytes;
+  ex->region_bytes = ex->ctl_off + align_up(sizeof(Ctl), 256);
+  auto cleanup = [&](int code) {
+    if (ex->local) cudaFree(ex->local);
+    if (ex->err_host) cudaFreeHost(ex->err_host);
     cudaGetLastError();
     delete ex;
-    return fail(MMR_ENOMEM, std::string("mmr_exchange_create: cudaMalloc: ") + cudaGetErrorString(e));
+    return code;
+  };
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->local), ex->region_bytes);
+  if (e != cudaSuccess) return cleanup(fail(MMR_ENOMEM, std::string("mmr_exchange_create: cudaMalloc: ") + cudaGetErrorString(e)));
+  e = cudaHostAlloc(reinterpret_cast<void**>(&ex->err_host), sizeof(uint32_t), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *ex->err_host = kErrNone;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ex->err_dev), ex->err_host, 0);
   }
-  e = cudaMemset(ex->local, 0, ex->region_bytes);
+  if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->region_bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) {
-    cudaFree(ex->local);
-    delete ex;
-    return fail(MMR_ECUDA, std::string("mmr_exchange_create: ") + cudaGetErrorString(e));
-  }
+  if (e != cudaSuccess) return cleanup(fail(MMR_ECUDA, std::string("mmr_exchange_create: ") + cudaGetErrorString(e)));
   for (int r = 0; r < kMaxWorld; ++r) ex->peers.base[r] = nullptr;
   ex->peers.base[rank] = ex->local;
   ex->open = world == 1;
@@ -307,111 +362,142 @@ int mmr_exchange_open(mmr_exchange* ex, const void* handles) {
   return MMR_OK;
 }
 
-int mmr_exchange_destroy(mmr_exchange* ex) {
+int mmr_exchange_set_timeout(mmr_exchange* ex, int32_t milliseconds) {
+  MMR_REQUIRE(ex != nullptr && milliseconds >= 1, "mmr_exchange_set_timeout: bad argument");
+  ex->timeout_ms = static_cast<uint32_t>(milliseconds);
+  return MMR_OK;
+}
+
+int mmr_exchange_status(mmr_exchange* ex, int32_t* code) {
+  MMR_REQUIRE(ex != nullptr, "mmr_exchange_status: exchange is NULL");
+  const uint32_t c = *reinterpret_cast<volatile uint32_t*>(ex->err_host);
+  if (code) *code = static_cast<int32_t>(c);
+  return c == kErrNone ? MMR_OK : check_call(ex, 1, 1, "mmr_exchange_status");
+}
+
+int mmr_exchange_abort(mmr_exchange* ex) {
+  // raise the abort word in every mapped region (ours included): kernels waiting on this exchange give up
+  MMR_REQUIRE(ex != nullptr, "mmr_exchange_abort: exchange is NULL");
+  DeviceGuard guard(ex->device);
+  cudaStream_t s = nullptr;
+  MMR_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));  // must not queue behind a spinning kernel
+  const uint32_t one = 1u;
+  cudaError_t e = cudaSuccess;
+  for (int r = 0; r < ex->world && e == cudaSuccess; ++r) {
+    if (ex->peers.base[r] == nullptr) continue;
+    e = cudaMemcpyAsync(ex->peers.base[r] + ex->ctl_off + offsetof(Ctl, abort), &one, sizeof(one), cudaMemcpyHostToDevice, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaStreamDestroy(s);
+  if (e != cudaSuccess) return fail(MMR_ECUDA, std::string("mmr_exchange_abort: ") + cudaGetErrorString(e));
+  return MMR_OK;
+}
+
+int mmr_exchange_close_peers(mmr_exchange* ex) {
+  // phase 1 of a shutdown: unmap every peer's region.  Callers put a barrier between this and
+  // mmr_exchange_destroy, which frees the region the peers had mapped (CUDA requires importers to close first).
   if (ex == nullptr) return MMR_OK;
   DeviceGuard guard(ex->device);
   cudaDeviceSynchronize();
   for (void* p : ex->opened) cudaIpcCloseMemHandle(p);
+  ex->opened.clear();
+  for (int r = 0; r < kMaxWorld; ++r)
+    if (r != ex->rank) ex->peers.base[r] = nullptr;
+  ex->open = false;
+  cudaGetLastError();
+  return MMR_OK;
+}
+
+int mmr_exchange_destroy(mmr_exchange* ex) {
+  if (ex == nullptr) return MMR_OK;
+  mmr_exchange_close_peers(ex);
+  DeviceGuard guard(ex->device);
   if (ex->local) cudaFree(ex->local);
+  if (ex->err_host) cudaFreeHost(ex->err_host);
   cudaGetLastError();
   delete ex;
   return MMR_OK;
 }
 
-int mmr_exchange_scatter(mmr_exchange* ex, const mmr_index* ix, const float* q_emb, const int64_t* rows,
-                         const float* scores, int32_t b, int32_t k, uint32_t step, void* stream_v) {
-  MMR_TRY(check_sizes(ex, b, k, "mmr_exchange_scatter"));
-  MMR_REQUIRE(ix && q_emb && rows && scores, "mmr_exchange_scatter: NULL argument");
-  if (!(is_device_ptr(q_emb) && is_device_ptr(rows) && is_device_ptr(scores)))
-    return fail(MMR_EINVAL, "mmr_exchange_scatter: device pointers only");
-  int64_t n = 0, row_offset = 0, bytes = 0;
-  int32_t d = 0, d_pad = 0, dtype = 0, device = 0;
-  MMR_TRY(mmr_index_info(ix, &n, &d, &d_pad, &dtype, &device, &row_offset, &bytes));
-  const void* emb = nullptr;
-  const float* inv = nullptr;
-  MMR_TRY(mmr_index_device_ptrs(ix, &emb, &inv));
-  if (dtype != MMR_BF16 || d_pad > 1024 || (reinterpret_cast<uintptr_t>(emb) & 15u) != 0)
-    return fail(MMR_EUNSUP, "mmr_exchange_scatter: needs a bf16 index with d <= 1024");
-  if (device != ex->device) return fail(MMR_EINVAL, "mmr_exchange_scatter: index and exchange live on different devices");
+int mmr_search_scatter(mmr_index* ix, mmr_exchange* ex, const void* q, int32_t b, int32_t q_dtype, int32_t k,
+                       int32_t algo, uint32_t step, void* stream_v) {
+  MMR_TRY(check_call(ex, b, k, "mmr_search_scatter"));
+  MMR_REQUIRE(ix != nullptr && q != nullptr, "mmr_search_scatter: NULL argument");
+  if (ix->device != ex->device) return fail(MMR_EINVAL, "mmr_search_scatter: index and exchange live on different devices");
+  const Layout L = layout_for(ex, b, k, k, step);
+  PeerSink sink;
+  sink.peers = ex->peers;
+  sink.off_scores = L.off_scores;
+  sink.off_rows = L.off_rows;
+  sink.per = L.per;
+  sink.kp = L.kp;
+  sink.my_rank = ex->rank;
+  MMR_TRY(search_impl(ix, q, b, q_dtype, k, algo, nullptr, nullptr, nullptr, &sink, stream_v));
   DeviceGuard guard(ex->device);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const Layout L = layout_for(ex, b, k, step);
-  const __nv_bfloat16* e16 = static_cast<const __nv_bfloat16*>(emb);
-  const int its = (d_pad + 255) / 256;
-#define MMR_XCHG(ITS)                                                                                              \
-  exchange_cos_scatter_kernel<ITS><<<b, 256, 0, stream>>>(e16, n, d_pad, row_offset, q_emb, d, rows, scores, k, L.kp, \
-                                                          L.per, ex->rank, ex->peers, L.off_scores, L.off_cos,       \
-                                                          L.off_rows)
-  if (its <= 1) {
-    MMR_XCHG(1);
-  } else if (its == 2) {
-    MMR_XCHG(2);
-  } else {
-    MMR_XCHG(4);
-  }
-#undef MMR_XCHG
-  MMR_LAUNCHED();
-  exchange_signal_kernel<<<1, 32, 0, stream>>>(ex->peers, ex->flags_off, 0, ex->world, ex->rank, step);
+  exchange_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_v)>>>(ex->peers, ex->ctl_off, 0, ex->world, ex->rank,
+                                                                            step, fingerprint(b, k));
   MMR_LAUNCHED();
   return MMR_OK;
 }
 
-int mmr_exchange_merge(mmr_exchange* ex, int32_t b, int32_t k, uint32_t step, float* out_scores, int64_t* out_rows,
-                       float* out_cos, void* stream_v) {
-  MMR_TRY(check_sizes(ex, b, k, "mmr_exchange_merge"));
+int mmr_exchange_rerank(mmr_exchange* ex, const mmr_rerank_tables* t, const int64_t* q_rec, int32_t b, int32_t k,
+                        double alpha, double beta, double gamma, int32_t topk, uint32_t step, const int64_t** ids,
+                        const double** fin, void* stream_v) {
+  MMR_TRY(check_call(ex, b, k, "mmr_exchange_rerank"));
+  MMR_REQUIRE(q_rec != nullptr && ids != nullptr && fin != nullptr && topk >= 0, "mmr_exchange_rerank: bad argument");
+  if (!is_device_ptr(q_rec)) return fail(MMR_EINVAL, "mmr_exchange_rerank: q_rec must be a device pointer");
+  if (t != nullptr && t->device != ex->device)
+    return fail(MMR_EINVAL, "mmr_exchange_rerank: tables and exchange live on different devices");
+  const TailTables tt{t ? t->masks : nullptr, t ? t->label_words : 0, t ? t->kg : nullptr, t ? t->d_kg : 0,
+                      t ? t->n_rec : 0};
+  if (!tail_supported(k, tt.kg, tt.d_kg) || ex->world * ((k + 3) / 4 * 4) > kMaxWorld * kTailMaxK)
+    return fail(MMR_EUNSUP, "mmr_exchange_rerank: needs k <= 128 and a KG dimension <= 512 that is a multiple of 4");
   DeviceGuard guard(ex->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const Layout L = layout_for(ex, b, k, step);
-  exchange_wait_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const uint32_t*>(ex->local + ex->flags_off), ex->world,
-                                             step);
-  MMR_LAUNCHED();
+  const int keep = (topk > 0 && topk < k) ? topk : k;
+  const Layout L = layout_for(ex, b, k, keep, step);
   const int q_lo = std::min(b, ex->rank * L.per), q_hi = std::min(b, (ex->rank + 1) * L.per);
-  const int nloc = q_hi - q_lo;
-  if (nloc <= 0) return MMR_OK;
-  MMR_REQUIRE(out_scores && out_rows && out_cos, "mmr_exchange_merge: NULL output");
-  if (!(is_device_ptr(out_scores) && is_device_ptr(out_rows) && is_device_ptr(out_cos)))
-    return fail(MMR_EINVAL, "mmr_exchange_merge: device pointers only");
-  const float* sc = reinterpret_cast<const float*>(ex->local + L.off_scores);
-  const float* co = reinterpret_cast<const float*>(ex->local + L.off_cos);
-  const int64_t* ro = reinterpret_cast<const int64_t*>(ex->local + L.off_rows);
-  int32_t* src = nullptr;
-  MMR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&src), static_cast<size_t>(nloc) * k * sizeof(int32_t), stream));
-  const int64_t stride = static_cast<int64_t>(L.per) * L.kp;
-  int st = launch_merge_lists(sc, ro, ex->world, nloc, L.kp, stride, stride, k, out_scores, out_rows, src, stream);
-  if (st == MMR_OK) st = launch_gather_payload(co, stride, src, nloc, L.kp, k, out_cos, stream);
-  cudaFreeAsync(src, stream);
-  return st;
-}
-
-int mmr_exchange_publish(mmr_exchange* ex, const int64_t* ids, const double* fin, int32_t b, int32_t keep,
-                         uint32_t step, void* stream_v) {
-  MMR_TRY(check_sizes(ex, b, keep, "mmr_exchange_publish"));
-  DeviceGuard guard(ex->device);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const Layout L = layout_for(ex, b, keep, step);
-  const int q_lo = std::min(b, ex->rank * L.per), q_hi = std::min(b, (ex->rank + 1) * L.per);
-  const int64_t count = static_cast<int64_t>(q_hi - q_lo) * keep;
-  if (count > 0) {
-    MMR_REQUIRE(ids && fin, "mmr_exchange_publish: NULL argument");
-    if (!(is_device_ptr(ids) && is_device_ptr(fin))) return fail(MMR_EINVAL, "mmr_exchange_publish: device pointers only");
-    exchange_publish_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, stream>>>(
-        ids, fin, count, static_cast<int64_t>(q_lo) * keep, ex->world, ex->peers, L.off_ids, L.off_fin);
+  const uint64_t timeout_ns = static_cast<uint64_t>(ex->timeout_ms) * 1000000ull;
+  Ctl* ctl = reinterpret_cast<Ctl*>(ex->local + ex->ctl_off);
+  if (q_hi > q_lo) {
+    RerankArgs a;
+    a.l_scores = reinterpret_cast<const float*>(ex->local + L.off_scores);
+    a.l_rows = reinterpret_cast<const int64_t*>(ex->local + L.off_rows);
+    a.ctl = ctl;
+    a.t = tt;
+    a.q_rec = q_rec;
+    a.q_lo = q_lo;
+    a.nloc = q_hi - q_lo;
+    a.b = b;
+    a.k = k;
+    a.kp = L.kp;
+    a.per = L.per;
+    a.world = ex->world;
+    a.my_rank = ex->rank;
+    a.keep = keep;
+    a.alpha = alpha;
+    a.beta = beta;
+    a.gamma = gamma;
+    a.peers = ex->peers;
+    a.off_ids = L.off_ids;
+    a.off_fin = L.off_fin;
+    a.ctl_off = ex->ctl_off;
+    a.step = step;
+    a.meta = fingerprint(b, k);
+    a.timeout_ns = timeout_ns;
+    a.err = ex->err_dev;
+    if (tt.kg == nullptr || tt.d_kg <= 384)
+      exchange_rerank_kernel<3><<<a.nloc, kTailThreads, 0, stream>>>(a);
+    else
+      exchange_rerank_kernel<4><<<a.nloc, kTailThreads, 0, stream>>>(a);
+    MMR_LAUNCHED();
+  } else {  // this rank owns no query of the batch: it still has to wait for the lists (buffer reuse) and signal
+    exchange_wait_kernel<<<1, 32, 0, stream>>>(ctl, 0, ex->world, step, timeout_ns, ex->err_dev);
+    MMR_LAUNCHED();
+    exchange_signal_kernel<<<1, 32, 0, stream>>>(ex->peers, ex->ctl_off, 1, ex->world, ex->rank, step, 0u);
     MMR_LAUNCHED();
   }
-  exchange_signal_kernel<<<1, 32, 0, stream>>>(ex->peers, ex->flags_off, 1, ex->world, ex->rank, step);
-  MMR_LAUNCHED();
-  return MMR_OK;
-}
-
-int mmr_exchange_collect(mmr_exchange* ex, int32_t b, int32_t keep, uint32_t step, const int64_t** ids,
-                         const double** fin, void* stream_v) {
-  MMR_TRY(check_sizes(ex, b, keep, "mmr_exchange_collect"));
-  MMR_REQUIRE(ids && fin, "mmr_exchange_collect: NULL argument");
-  DeviceGuard guard(ex->device);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const Layout L = layout_for(ex, b, keep, step);
-  exchange_wait_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const uint32_t*>(ex->local + ex->flags_off) + ex->world,
-                                             ex->world, step);
+  exchange_wait_kernel<<<1, 32, 0, stream>>>(ctl, 1, ex->world, step, timeout_ns, ex->err_dev);
   MMR_LAUNCHED();
   *ids = reinterpret_cast<const int64_t*>(ex->local + L.off_ids);
   *fin = reinterpret_cast<const double*>(ex->local + L.off_fin);

@@ -20,6 +20,21 @@ struct DeviceBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// Multi-GPU exchange (exchange.cu): base address of every rank's region as mapped into THIS process, and the
+// description of where a select kernel puts a query's top-k when the result goes straight to the rank that
+// owns the query (list-major layout [source rank][local query][kp], see exchange.cu).
+constexpr int kMaxWorld = 16;
+struct PeerTable {
+  uint8_t* base[kMaxWorld];
+};
+struct PeerSink {
+  PeerTable peers;
+  size_t off_scores, off_rows;  // byte offsets of the fp32 score / int64 row lists inside every region
+  int per;                      // queries per owner rank (owner of q = q / per)
+  int kp;                       // padded list length (multiple of 4, >= k)
+  int my_rank;                  // this rank = the list index at the owner
+};
+
 bool is_device_ptr(const void* p);
 int elem_size(int dtype);
 
@@ -63,8 +78,10 @@ int launch_scan(const void* emb, int dtype_store, const float* inv_norm, int64_t
                 const ScanPlan& plan, uint64_t* partial, cudaStream_t stream);
 
 // select.cu: per query, top `k_out` of `n_parts * kp` keys -> (score, global row), best first.
+// `sink` != nullptr: the lists are stored into the owner ranks' exchange regions instead of out_scores /
+// out_rows (which then serve as staging when the fused kernel does not cover the shape).
 int launch_select_keys(const uint64_t* keys, int b, int64_t keys_per_query, int k_out, int64_t row_offset,
-                       float* out_scores, int64_t* out_rows, cudaStream_t stream);
+                       float* out_scores, int64_t* out_rows, cudaStream_t stream, const PeerSink* sink = nullptr);
 // select.cu: merge (n_lists, b, k_in) (score,row) lists -> (b, k_out); out_src optional.
 int launch_merge_lists(const float* scores, const int64_t* rows, int n_lists, int b, int k_in,
                        int64_t scores_list_stride, int64_t rows_list_stride, int k_out, float* out_scores,
@@ -103,7 +120,9 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
                      uint64_t* cand, int32_t* counts, uint32_t* tau_pub, cudaStream_t stream);
 int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int per_part,
                       int k_out, int64_t row_offset, const int64_t* exclude_local, const uint32_t* tau_pub, int b_pad,
-                      float* out_scores, int64_t* out_rows, cudaStream_t stream);
+                      float* out_scores, int64_t* out_rows, cudaStream_t stream, const PeerSink* sink = nullptr);
+// select.cu: (b, k) dense lists -> the owners' regions (fallback of the fused select + scatter)
+int launch_scatter_lists(const float* scores, const int64_t* rows, int b, int k, const PeerSink& sink, cudaStream_t stream);
 
 // rerank.cu
 int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pad, int64_t row_offset,
@@ -115,6 +134,14 @@ int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pa
 int launch_rerank_combine(const double* raw, const int32_t* cand_count, int b, int k, double alpha,
                           double beta, double gamma, int topk, int32_t* out_order, double* out_scores,
                           cudaStream_t stream);
+
+// rerank.cu: the fused tail (features + min-max + combine + order) of a search result whose embedding
+// feature is the search score; candidates' record index == their GLOBAL row id.
+bool tail_supported(int k, const void* kg, int d_kg);
+int launch_rerank_scored(const int64_t* rows, const float* scores, const int64_t* q_rec, const uint64_t* masks,
+                         int label_words, const float* kg, int d_kg, int64_t n_rec, int b, int k, double alpha,
+                         double beta, double gamma, int topk, int64_t* out_ids, double* out_fin,
+                         double* out_scores4, cudaStream_t stream);
 
 // metrics.cu
 int launch_metrics(const int64_t* retrieved, const int32_t* ret_count, int q, int k_ret,
@@ -134,3 +161,53 @@ int launch_diversity(const float* emb, const uint64_t* masks, const int32_t* cou
                      double* out_emb_div, double* out_label_div, cudaStream_t stream);
 
 }  // namespace mmr
+
+// ------------------------------------------------------------------------------------------------
+// handles (opaque in the C ABI; shared by the translation units of the library)
+// ------------------------------------------------------------------------------------------------
+#include <vector>
+
+struct mmr_index {
+  int device = 0;
+  int num_sms = 148;
+  int64_t n = 0;
+  int d = 0, d_pad = 0;
+  int dtype = MMR_BF16;
+  int64_t row_offset = 0;
+  void* emb = nullptr;
+  bool owns_emb = true;
+  float* inv_norm = nullptr;
+  // Re-entrancy: the grow-only workspaces below are one set per handle.  `mu` serialises the host side of
+  // a call; `last_done` (recorded at the end of every call on its stream) makes the NEXT call's stream
+  // wait for the previous call's kernels, so two threads / streams sharing one handle never overlap on
+  // the device either (calls with host outputs synchronise anyway).
+  std::mutex mu;
+  cudaEvent_t last_done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  mmr::GemmTune tune;
+  int last_algo = 0, last_variant = 0, last_pair = 0, last_parts = 0, last_tiles_per_part = 0;
+  mmr::DeviceBuf q_in, q_store, q_f32, q_inv, scratch, excl_in, excl_local, partial, counts, tau_pub, out_scores, out_rows;
+  // live kernel timing (mmr_index_profile)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_start, ev_stop;
+  size_t ev_used = 0;
+};
+
+struct mmr_rerank_tables {
+  int device = 0;
+  int64_t n_rec = 0;
+  int label_words = 0;
+  int d_kg = 0;
+  uint64_t* masks = nullptr;
+  float* kg = nullptr;
+};
+
+namespace mmr {
+// api.cu: the body of mmr_search; with `sink` the lists go to the owner ranks' exchange regions.
+int search_impl(mmr_index* ix, const void* q, int32_t b, int32_t q_dtype, int32_t k, int32_t algo,
+                const int64_t* exclude_rows, float* out_scores, int64_t* out_rows, const PeerSink* sink,
+                void* stream);
+int check_device(int device, int* num_sms);
+}  // namespace mmr
+

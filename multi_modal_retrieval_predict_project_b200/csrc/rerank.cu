@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include "internal.h"
+#include "rerank_tail.cuh"
 
 namespace mmr {
 namespace {
@@ -408,7 +409,73 @@ rerank_combine_kernel(const double* __restrict__ raw, const int32_t* __restrict_
   }
 }
 
+// Single-shard fused tail: one CTA per query; candidates = the search result (rows, scores) (b, k), best first,
+// -1 rows = padding.  Writes what retrieve(..., reranker=...) returns (Retrieval/retrieval.py:257-269): ids in
+// reranked order + combined scores (b, keep), optionally the four score columns of Reranker.rerank's tuples.
+template <int kKIts>
+__global__ void __launch_bounds__(kTailThreads)
+rerank_scored_kernel(const int64_t* __restrict__ rows, const float* __restrict__ scores,
+                     const int64_t* __restrict__ q_rec, TailTables t, int k, double alpha, double beta, double gamma,
+                     int keep, int64_t* __restrict__ out_ids, double* __restrict__ out_fin,
+                     double* __restrict__ out_scores4) {
+  __shared__ TailSmem sm;
+  __shared__ int s_count;
+  const int q = blockIdx.x;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < k) {
+    const int64_t r = rows[static_cast<int64_t>(q) * k + threadIdx.x];
+    sm.cand_row[threadIdx.x] = r;
+    sm.cand_score[threadIdx.x] = scores[static_cast<int64_t>(q) * k + threadIdx.x];
+    if (r >= 0) atomicAdd(&s_count, 1);   // valid candidates form a prefix (search pads at the end)
+  }
+  __syncthreads();
+  const int count = s_count;
+  const int64_t base = static_cast<int64_t>(q) * keep;
+  rerank_tail<kKIts>(sm, count, q_rec != nullptr ? q_rec[q] : -1, t, alpha, beta, gamma, keep,
+                     [&](int rank, int j, double fin, double e, double l, double g) {
+                       out_ids[base + rank] = sm.cand_row[j];
+                       out_fin[base + rank] = fin;
+                       if (out_scores4 != nullptr) {
+                         double* o = out_scores4 + (base + rank) * 4;
+                         o[0] = fin; o[1] = e; o[2] = l; o[3] = g;
+                       }
+                     });
+  for (int r = count + threadIdx.x; r < keep; r += kTailThreads) {  // fewer valid candidates than `keep`
+    out_ids[base + r] = -1;
+    out_fin[base + r] = 0.0;
+    if (out_scores4 != nullptr) {
+      double* o = out_scores4 + (base + r) * 4;
+      o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0;
+    }
+  }
+}
+
 }  // namespace
+
+// KG table shapes the fused tail covers (else callers use the unfused kernels)
+bool tail_supported(int k, const void* kg, int d_kg) {
+  return k >= 1 && k <= kTailMaxK &&
+         (kg == nullptr || (d_kg % 4 == 0 && d_kg <= 512 && (reinterpret_cast<uintptr_t>(kg) & 15u) == 0));
+}
+
+int launch_rerank_scored(const int64_t* rows, const float* scores, const int64_t* q_rec, const uint64_t* masks,
+                         int label_words, const float* kg, int d_kg, int64_t n_rec, int b, int k, double alpha,
+                         double beta, double gamma, int topk, int64_t* out_ids, double* out_fin,
+                         double* out_scores4, cudaStream_t stream) {
+  if (b == 0 || k == 0) return MMR_OK;
+  if (!tail_supported(k, kg, d_kg)) return fail(MMR_EUNSUP, "rerank_scored: needs k <= 128 and a KG dimension <= 512 that is a multiple of 4");
+  const int keep = (topk > 0 && topk < k) ? topk : k;
+  const TailTables t{masks, label_words, kg, d_kg, n_rec};
+  if (kg == nullptr || d_kg <= 384)
+    rerank_scored_kernel<3><<<b, kTailThreads, 0, stream>>>(rows, scores, q_rec, t, k, alpha, beta, gamma, keep, out_ids,
+                                                            out_fin, out_scores4);
+  else
+    rerank_scored_kernel<4><<<b, kTailThreads, 0, stream>>>(rows, scores, q_rec, t, k, alpha, beta, gamma, keep, out_ids,
+                                                            out_fin, out_scores4);
+  MMR_LAUNCHED();
+  return MMR_OK;
+}
 
 int launch_rerank_features(const void* emb, int dtype_store, int64_t n, int d_pad, int64_t row_offset,
                            const uint64_t* label_masks, int label_words, const float* kg, int d_kg, int64_t n_rec,

@@ -224,10 +224,40 @@ struct TauBound {  // tau_pub[list][b_pad] of ordered-u32 scores, 0 = not publis
 };
 constexpr int kRankCap = 512;
 
-template <typename Source, typename Bound>
+// Where the selected (score, global row) pairs go: dense (b, k_out) arrays, or -- the fused select + scatter
+// of the sharded path -- straight into the exchange region of the rank that owns the query (16 x 4/8-byte
+// NVLink stores per query instead of a second kernel that re-reads the dense arrays).
+struct DenseSink {
+  float* scores;
+  int64_t* rows;
+  int32_t* src;
+  int k_out;
+  __device__ __forceinline__ int limit() const { return k_out; }
+  __device__ __forceinline__ void put(int q, int r, float score, int64_t row, int32_t from) const {
+    const int64_t o = static_cast<int64_t>(q) * k_out + r;
+    scores[o] = score;
+    rows[o] = row;
+    if (src != nullptr) src[o] = from;
+  }
+  __device__ __forceinline__ void pad(int q, int r) const { put(q, r, -INFINITY, -1, -1); }
+  __device__ __forceinline__ void finish() const {}
+};
+struct RemoteSink {
+  PeerSink s;
+  __device__ __forceinline__ int limit() const { return s.kp; }
+  __device__ __forceinline__ void put(int q, int r, float score, int64_t row, int32_t) const {
+    const int dest = q / s.per;
+    const int64_t slot = (static_cast<int64_t>(s.my_rank) * s.per + (q - dest * s.per)) * s.kp + r;
+    reinterpret_cast<float*>(s.peers.base[dest] + s.off_scores)[slot] = score;
+    reinterpret_cast<int64_t*>(s.peers.base[dest] + s.off_rows)[slot] = row;
+  }
+  __device__ __forceinline__ void pad(int q, int r) const { put(q, r, -INFINITY, -1, -1); }
+  __device__ __forceinline__ void finish() const { __threadfence_system(); }  // before the signal kernel's release
+};
+
+template <typename Source, typename Bound, typename Sink>
 __global__ void __launch_bounds__(256)
-select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, float* __restrict__ out_scores,
-                   int64_t* __restrict__ out_rows, int32_t* __restrict__ out_src, uint64_t* __restrict__ stage_keys) {
+select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, Sink sink, uint64_t* __restrict__ stage_keys) {
   __shared__ __align__(16) uint64_t lvl2[8 * 128];
   __shared__ int32_t lvl2_idx[8 * 128];
   __shared__ __align__(16) uint64_t fin[128];
@@ -289,19 +319,12 @@ select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, float
       for (int h = 0; h < 2; ++h) {
         const uint64_t k64 = h == 0 ? k0 : k1;
         const int r = h == 0 ? r0 : r1;
-        if (k64 != 0ull && r < k_out) {
-          const int64_t o = static_cast<int64_t>(q) * k_out + r;
-          out_scores[o] = key_score(k64);
-          out_rows[o] = row_offset + static_cast<int64_t>(key_row(k64));
-          if (out_src != nullptr) out_src[o] = lvl2_idx[threadIdx.x + h * 256];
-        }
+        if (k64 != 0ull && r < k_out)
+          sink.put(q, r, key_score(k64), row_offset + static_cast<int64_t>(key_row(k64)), lvl2_idx[threadIdx.x + h * 256]);
       }
-      for (int i = m + threadIdx.x; i < k_out; i += blockDim.x) {  // fewer candidates than k_out
-        const int64_t o = static_cast<int64_t>(q) * k_out + i;
-        out_scores[o] = -INFINITY;
-        out_rows[o] = -1;
-        if (out_src != nullptr) out_src[o] = -1;
-      }
+      // fewer candidates than k_out, and the sink's padding beyond k_out
+      for (int i = (m < k_out ? m : k_out) + threadIdx.x; i < sink.limit(); i += blockDim.x) sink.pad(q, i);
+      sink.finish();
       return;
     }
     __syncthreads();  // lvl2 is reused below
@@ -330,20 +353,28 @@ select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, float
       return;
     }
     warp_bitonic_sort_desc_kv(fin, fin_idx, 128, lane);
-    for (int i = lane; i < k_out; i += 32) {
-      const uint64_t k64 = fin[i];
-      const int64_t o = static_cast<int64_t>(q) * k_out + i;
-      if (k64 == 0ull) {
-        out_scores[o] = -INFINITY;
-        out_rows[o] = -1;
-        if (out_src != nullptr) out_src[o] = -1;
-      } else {
-        out_scores[o] = key_score(k64);
-        out_rows[o] = row_offset + static_cast<int64_t>(key_row(k64));
-        if (out_src != nullptr) out_src[o] = fin_idx[i];
-      }
+    for (int i = lane; i < sink.limit(); i += 32) {
+      const uint64_t k64 = (i < k_out) ? fin[i] : 0ull;
+      if (k64 == 0ull)
+        sink.pad(q, i);
+      else
+        sink.put(q, i, key_score(k64), row_offset + static_cast<int64_t>(key_row(k64)), fin_idx[i]);
     }
+    sink.finish();
   }
+}
+
+// dense (b, k) lists -> the owner ranks' regions (shapes the fused select + scatter does not cover)
+__global__ void scatter_lists_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows, int b, int k,
+                                     RemoteSink sink) {
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < sink.limit(); i += blockDim.x) {
+    if (i < k && rows[static_cast<int64_t>(q) * k + i] >= 0)
+      sink.put(q, i, scores[static_cast<int64_t>(q) * k + i], rows[static_cast<int64_t>(q) * k + i], -1);
+    else
+      sink.pad(q, i);
+  }
+  sink.finish();
 }
 
 // payload carried through a merge: out[q][i] = payload[list * stride + q * k_in + j] for the source
@@ -373,11 +404,23 @@ __global__ void apply_order_kernel(const int64_t* __restrict__ rows, const int32
 
 template <typename Source, typename Bound = NoBound>
 int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_offset, float* out_scores,
-                  int64_t* out_rows, int32_t* out_src, cudaStream_t stream, Bound bound = Bound()) {
+                  int64_t* out_rows, int32_t* out_src, cudaStream_t stream, Bound bound = Bound(),
+                  const PeerSink* peer = nullptr) {
   if (b == 0 || k_out == 0) return MMR_OK;
+  if (peer != nullptr) {
+    if (k_out <= 128 && per_query <= 4096) {  // fused: the selection's output stores ARE the exchange
+      select_fast_kernel<Source, Bound, RemoteSink><<<b, 256, 0, stream>>>(src, bound, k_out, row_offset,
+                                                                          RemoteSink{*peer}, nullptr);
+      MMR_LAUNCHED();
+      return MMR_OK;
+    }
+    MMR_REQUIRE(out_scores != nullptr && out_rows != nullptr, "select: staging buffers needed for the scatter");
+    MMR_TRY(launch_select(src, b, per_query, k_out, row_offset, out_scores, out_rows, nullptr, stream, bound, nullptr));
+    return launch_scatter_lists(out_scores, out_rows, b, k_out, *peer, stream);
+  }
   if (k_out <= 128 && per_query <= 4096) {
-    select_fast_kernel<Source, Bound><<<b, 256, 0, stream>>>(src, bound, k_out, row_offset, out_scores, out_rows,
-                                                             out_src, nullptr);
+    select_fast_kernel<Source, Bound, DenseSink><<<b, 256, 0, stream>>>(
+        src, bound, k_out, row_offset, DenseSink{out_scores, out_rows, out_src, k_out}, nullptr);
     MMR_LAUNCHED();
     return MMR_OK;
   }
@@ -387,12 +430,12 @@ int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_o
     uint64_t* stage = nullptr;
     MMR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&stage), static_cast<size_t>(b) * chunks * 128 * sizeof(uint64_t),
                                  stream));
-    select_fast_kernel<Source, Bound><<<dim3(b, chunks), 256, 0, stream>>>(src, bound, k_out, row_offset, nullptr,
-                                                                          nullptr, nullptr, stage);
+    select_fast_kernel<Source, Bound, DenseSink><<<dim3(b, chunks), 256, 0, stream>>>(
+        src, bound, k_out, row_offset, DenseSink{nullptr, nullptr, nullptr, k_out}, stage);
     count_launch();
     KeySourceFlat flat{stage, static_cast<int64_t>(chunks) * 128};
-    select_fast_kernel<KeySourceFlat, NoBound><<<b, 256, 0, stream>>>(flat, NoBound(), k_out, row_offset, out_scores,
-                                                                     out_rows, nullptr, nullptr);
+    select_fast_kernel<KeySourceFlat, NoBound, DenseSink><<<b, 256, 0, stream>>>(
+        flat, NoBound(), k_out, row_offset, DenseSink{out_scores, out_rows, nullptr, k_out}, nullptr);
     count_launch();
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(stage, stream);
@@ -422,18 +465,27 @@ int launch_select(Source src, int b, int64_t per_query, int k_out, int64_t row_o
 }  // namespace
 
 int launch_select_keys(const uint64_t* keys, int b, int64_t keys_per_query, int k_out, int64_t row_offset,
-                       float* out_scores, int64_t* out_rows, cudaStream_t stream) {
+                       float* out_scores, int64_t* out_rows, cudaStream_t stream, const PeerSink* sink) {
   KeySourceFlat src{keys, keys_per_query};
-  return launch_select(src, b, keys_per_query, k_out, row_offset, out_scores, out_rows, nullptr, stream);
+  return launch_select(src, b, keys_per_query, k_out, row_offset, out_scores, out_rows, nullptr, stream, NoBound(),
+                       sink);
+}
+
+int launch_scatter_lists(const float* scores, const int64_t* rows, int b, int k, const PeerSink& sink,
+                         cudaStream_t stream) {
+  if (b == 0) return MMR_OK;
+  scatter_lists_kernel<<<b, 128, 0, stream>>>(scores, rows, b, k, RemoteSink{sink});
+  MMR_LAUNCHED();
+  return MMR_OK;
 }
 
 int launch_select_var(const uint64_t* cand, const int32_t* counts, int b, int n_parts, int cap, int per_part,
                       int k_out, int64_t row_offset, const int64_t* exclude_local, const uint32_t* tau_pub, int b_pad,
-                      float* out_scores, int64_t* out_rows, cudaStream_t stream) {
+                      float* out_scores, int64_t* out_rows, cudaStream_t stream, const PeerSink* sink) {
   KeySourceVar src{reinterpret_cast<const uint2*>(cand), counts, n_parts, cap, per_part, exclude_local};
   TauBound bound{tau_pub, n_parts, b_pad};
   return launch_select(src, b, static_cast<int64_t>(n_parts) * per_part, k_out, row_offset, out_scores, out_rows,
-                       nullptr, stream, bound);
+                       nullptr, stream, bound, sink);
 }
 
 int launch_gather_payload(const float* payload, int64_t list_stride, const int32_t* src, int b, int k_in, int k_out,

@@ -89,14 +89,35 @@ class PeerExchange:
                 except Exception as e:  # noqa: BLE001
                     self.error = str(e)
 
-    def close(self):
+    def check(self):
+        """Raise if a device-side wait of an earlier step gave up (timeout, abort, (b, k) mismatch)."""
         if getattr(self, "_h", None) is not None and self._h.value:
-            self._lib.mmr_exchange_destroy(self._h)
-            self._h = None
+            _lib.check(self._lib.mmr_exchange_status(self._h, None))
+
+    def abort(self):
+        """Make every kernel that waits on this exchange -- here and on the peers -- give up at once."""
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mmr_exchange_abort(self._h)
+
+    def close(self, group=None, collective: bool = True):
+        """Two-phase shutdown (collective: every rank calls it): unmap the peers' regions, barrier, then free
+        this rank's region -- CUDA requires importers to close their mappings before the exporter frees.
+        ``collective=False`` (interpreter exit, a peer is gone) skips the barrier."""
+        if getattr(self, "_h", None) is None or not self._h.value:
+            return
+        import torch.distributed as dist
+        self._lib.mmr_exchange_close_peers(self._h)
+        if collective and self.world > 1 and dist.is_available() and dist.is_initialized():
+            try:
+                dist.barrier(group=group)
+            except Exception:  # noqa: BLE001
+                pass
+        self._lib.mmr_exchange_destroy(self._h)
+        self._h = None
 
     def __del__(self):
         try:
-            self.close()
+            self.close(collective=False)
         except Exception:
             pass
 
@@ -149,7 +170,10 @@ class ShardedSearcher:
         scores_v, cos_v = f[:bk].view(b, K), f[bk:].view(b, K)
         rows_v = self._blob[bk * 8:].view(torch.int64).view(b, K)
         eng.search(queries, K, algo=algo, out_rows=rows_v, out_scores=scores_v)
-        reranker.candidate_cosine_device(eng, queries, rows_v, out=cos_v)
+        if getattr(reranker, "emb_feature", "search_score") == "search_score":
+            cos_v.copy_(scores_v)     # the rerank's embedding feature IS the search score (reranker.py:298)
+        else:
+            reranker.candidate_cosine_device(eng, queries, rows_v, out=cos_v)
         dist.all_gather_into_tensor(self._gblob, self._blob, group=self.group)
         return self._gblob
 
@@ -178,17 +202,20 @@ class ShardedSearcher:
         return out_r, out_s, cos
 
     def search_rerank(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
-        """The whole sharded step with ONE collective.  Every rank: local top-K, the fp32 embedding
-        cosine of its own K candidates (all rows are local), then a single NCCL all-gather of one
-        blob per rank ``[scores f32 | cosines f32 | rows i64]``; the strided on-device merge reads
-        the gathered blobs in place and reports where each winner came from, the cosines follow
-        through that index, and label/KG features come from the replicated tables.  The record index
-        of a candidate is its global row id.  Returns ``(rows, scores, order, rerank_scores)``."""
+        """The whole sharded step with ONE collective.  Every rank: local top-K (+ the embedding feature of
+        its own K candidates), then a single NCCL all-gather of one blob per rank ``[scores f32 | cosines
+        f32 | rows i64]``; the strided on-device merge reads the gathered blobs in place and reports where
+        each winner came from, the cosines follow through that index, and label/KG features come from the
+        replicated tables.  The record index of a candidate is its global row id.  Returns ``(rows,
+        scores, order, rerank_scores)``."""
         eng = self.engine
         b = int(queries.shape[0])
         if self.world == 1:
             rows, scores = eng.search(queries, K, algo=algo)
-            order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
+            if getattr(reranker, "emb_feature", "search_score") == "search_score":
+                order, sc = reranker.rerank_with_cos_device(scores, q_rec, rows, topk)
+            else:
+                order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
             return rows, scores, order, sc
         gblob = self._local_blob(reranker, queries, K, algo)
         out_r, out_s, cos = self._merge_slice(gblob, b, K, 0, b)
@@ -197,13 +224,17 @@ class ShardedSearcher:
 
     def retrieve_reranked(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
         """What ``retrieve(q, K, reranker=..., query_id=...)`` returns (Retrieval/retrieval.py:257-269)
-        for a batch: ``(ids (B, keep) int64 in reranked order, combined scores (B, keep) fp64)``.
-        Sharded: every rank merges and reranks only ITS slice of the queries (the post-processing is
-        split G ways instead of replicated) and every rank ends with the full result.  With the
-        peer exchange (default) the local lists and the result slices move with NVLink stores issued
-        by the kernels themselves (csrc/exchange.cu) and the returned tensors are views of this
-        rank's exchange region, valid until the call after next; otherwise one NCCL all-gather of
-        the per-rank blobs and two of the result slices."""
+        for a batch: ``(ids (B, keep) int64 in reranked order, combined scores (B, keep) fp64)``.  The record
+        index of a candidate is its global row id; the rerank's embedding feature (reranker.py:298) is the
+        search score unless ``reranker.emb_feature == "recompute"``.
+
+        Single shard: search -> ONE fused kernel (features, min-max, combine, order; ``mmr_rerank_scored``).
+        Sharded: every rank merges and reranks only ITS slice of the queries and every rank ends with the
+        full result.  With the peer exchange (default) the search's selection kernel stores the local lists
+        straight into the owner ranks' memory and one kernel per owner merges, reranks and publishes
+        (csrc/exchange.cu); the returned tensors are views of this rank's exchange region, valid until the
+        call after next.  Otherwise (``use_peer=False``, K > 128, fp32 index ...): one NCCL all-gather of the
+        per-rank blobs and two of the result slices."""
         import torch
         import torch.distributed as dist
         eng = self.engine
@@ -212,9 +243,15 @@ class ShardedSearcher:
         dev = queries.device
         d = dev.index or 0
         lib = _lib.load()
+        by_score = getattr(reranker, "emb_feature", "search_score") == "search_score"
         if self.world == 1:
-            rows, _scores = eng.search(queries, K, algo=algo)
-            order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
+            rows, scores = eng.search(queries, K, algo=algo)
+            if by_score and reranker.fused_tail_ok(K):
+                return reranker.rerank_scored_device(rows, scores, q_rec, topk)
+            if by_score:
+                order, sc = reranker.rerank_with_cos_device(scores, q_rec, rows, topk)
+            else:
+                order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
             ids = torch.empty((b, keep), dtype=torch.int64, device=dev)
             fin = torch.empty((b, keep), dtype=torch.float64, device=dev)
             with torch.cuda.device(d):
@@ -224,36 +261,25 @@ class ShardedSearcher:
         rank = dist.get_rank(self.group)
         per = (b + self.world - 1) // self.world
         q_lo, q_hi = min(b, rank * per), min(b, (rank + 1) * per)
-        nloc = q_hi - q_lo
-        px = self._peer_exchange(b, K, queries)
+        px = self._peer_exchange(b, K, queries, reranker) if by_score else None
         if px is not None:
             # ---- NVLink peer-memory path: no collective call between search and result ----
             import ctypes as C
-            if getattr(self, "_loc", None) is None or self._loc[0].shape != (b, K):
-                self._loc = (torch.empty((b, K), dtype=torch.int64, device=dev),
-                             torch.empty((b, K), dtype=torch.float32, device=dev))
-            rows_l, scores_l = self._loc
-            eng.search(queries, K, algo=algo, out_rows=rows_l, out_scores=scores_l)
             px.step += 1
             step = px.step
+            q = queries.detach()
+            qd = _lib.MMR_BF16 if q.dtype == torch.bfloat16 else _lib.MMR_F32
+            if qd == _lib.MMR_F32:
+                q = q.float()
+            q = q.contiguous()
+            a = _lib.ALGOS[algo if algo is not None else eng.algo]
             with torch.cuda.device(d):
                 st = _lib.current_stream(d)
-                _lib.check(lib.mmr_exchange_scatter(px._h, eng._handle, _lib.ptr(queries), _lib.ptr(rows_l),
-                                                    _lib.ptr(scores_l), b, K, step, st))
-                out_s = torch.empty((max(nloc, 1), K), dtype=torch.float32, device=dev)
-                out_r = torch.empty((max(nloc, 1), K), dtype=torch.int64, device=dev)
-                cos = torch.empty((max(nloc, 1), K), dtype=torch.float32, device=dev)
-                _lib.check(lib.mmr_exchange_merge(px._h, b, K, step, _lib.ptr(out_s), _lib.ptr(out_r), _lib.ptr(cos), st))
-                ids = fin = None
-                if nloc > 0:
-                    order, sc = reranker.rerank_with_cos_device(cos[:nloc], q_rec[q_lo:q_hi], out_r[:nloc], topk)
-                    ids = torch.empty((nloc, keep), dtype=torch.int64, device=dev)
-                    fin = torch.empty((nloc, keep), dtype=torch.float64, device=dev)
-                    _lib.check(lib.mmr_apply_order(_lib.ptr(out_r), _lib.ptr(order), _lib.ptr(sc), nloc, K, keep,
-                                                   _lib.ptr(ids), _lib.ptr(fin), d, st))
-                _lib.check(lib.mmr_exchange_publish(px._h, _lib.ptr(ids), _lib.ptr(fin), b, keep, step, st))
+                _lib.check(lib.mmr_search_scatter(eng._handle, px._h, _lib.ptr(q), b, qd, K, a, step, st))
                 p_ids, p_fin = C.c_void_p(), C.c_void_p()
-                _lib.check(lib.mmr_exchange_collect(px._h, b, keep, step, C.byref(p_ids), C.byref(p_fin), st))
+                _lib.check(lib.mmr_exchange_rerank(px._h, reranker._tables, _lib.ptr(q_rec), b, K, reranker.alpha,
+                                                   reranker.beta, reranker.gamma, int(topk), step, C.byref(p_ids),
+                                                   C.byref(p_fin), st))
             # the full (b, keep) result lives in this rank's exchange region until step + 2
             return (_lib.as_cuda_tensor(p_ids.value, (b, keep), torch.int64, d),
                     _lib.as_cuda_tensor(p_fin.value, (b, keep), torch.float64, d))
@@ -266,11 +292,15 @@ class ShardedSearcher:
                          torch.zeros((per, keep), dtype=torch.float64, device=dev))
         all_ids, all_fin, my_ids, my_fin = self._fin
         if q_hi > q_lo:
-            out_r, _out_s, cos = self._merge_slice(gblob, b, K, q_lo, q_hi)
-            order, sc = reranker.rerank_with_cos_device(cos, q_rec[q_lo:q_hi], out_r, topk)
-            with torch.cuda.device(d):
-                _lib.check(lib.mmr_apply_order(_lib.ptr(out_r), _lib.ptr(order), _lib.ptr(sc), q_hi - q_lo, K, keep,
-                                               _lib.ptr(my_ids), _lib.ptr(my_fin), d, _lib.current_stream(d)))
+            out_r, out_s, cos = self._merge_slice(gblob, b, K, q_lo, q_hi)
+            if by_score and reranker.fused_tail_ok(K):
+                reranker.rerank_scored_device(out_r, cos, q_rec[q_lo:q_hi], topk,
+                                              out=(my_ids[: q_hi - q_lo], my_fin[: q_hi - q_lo]))
+            else:
+                order, sc = reranker.rerank_with_cos_device(cos, q_rec[q_lo:q_hi], out_r, topk)
+                with torch.cuda.device(d):
+                    _lib.check(lib.mmr_apply_order(_lib.ptr(out_r), _lib.ptr(order), _lib.ptr(sc), q_hi - q_lo, K, keep,
+                                                   _lib.ptr(my_ids), _lib.ptr(my_fin), d, _lib.current_stream(d)))
         dist.all_gather_into_tensor(all_ids, my_ids, group=self.group)
         dist.all_gather_into_tensor(all_fin, my_fin, group=self.group)
         return all_ids[:b], all_fin[:b]
@@ -335,14 +365,15 @@ class ShardedSearcher:
             ev_out[pending[0]].synchronize()
             yield pending[1]
 
-    def _peer_exchange(self, b: int, K: int, queries):
+    def _peer_exchange(self, b: int, K: int, queries, reranker=None):
         """The NVLink peer-memory exchange for (b, K), created on first use (collective: every rank
-        calls with the same sizes).  ``use_peer=False`` or MMR_B200_NO_PEER=1 selects the NCCL path;
-        indexes the fused scatter kernel does not cover (fp32 storage, d > 1024) use NCCL as well."""
+        calls with the same sizes).  ``use_peer=False`` or MMR_B200_NO_PEER=1 selects the NCCL path; shapes
+        the fused kernels do not cover (K > 128, more than 16 ranks, KG dimension > 512 or not a multiple of
+        4) use NCCL as well."""
         import os
         if not self.use_peer or os.environ.get("MMR_B200_NO_PEER") == "1" or self.world > 16:
             return None
-        if self.engine.dtype != "bfloat16" or int(queries.shape[1]) > 1024 or K > _lib.MAX_K:
+        if K > 128 or (reranker is not None and not reranker.fused_tail_ok(K)):
             return None
         px = getattr(self, "_px", None)
         if px is None or px.b_max < b or px.k_max < K:
@@ -350,7 +381,7 @@ class ShardedSearcher:
             import torch
             import torch.distributed as dist
             if px is not None:
-                px.close()
+                px.close(group=self.group)          # views returned by earlier calls are invalid from here on
             b_max, k_max = max(b, px.b_max if px else 0), max(K, px.k_max if px else 0)
             # creating the regions and mapping the peers is collective; if ANY rank cannot map its peers
             # (no P2P between the devices, IPC disabled) every rank falls back to the NCCL transport together
@@ -360,8 +391,7 @@ class ShardedSearcher:
             # (also the barrier: every rank has mapped every region before anybody stores into one)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
             if int(flag.item()) == 0:
-                if px is not None:
-                    px.close()
+                px.close(group=self.group)
                 print(f"[mmr_b200] NVLink peer exchange unavailable ({err or 'a peer rank failed'}); "
                       "using the NCCL all-gather transport", file=sys.stderr)
                 self.use_peer = False
@@ -369,6 +399,12 @@ class ShardedSearcher:
                 return None
             self._px = px
         return px
+
+    def close(self):
+        """Release the peer exchange (collective at world > 1: unmap, barrier, free)."""
+        px, self._px = getattr(self, "_px", None), None
+        if px is not None:
+            px.close(group=self.group)
 
     def rerank(self, reranker, q_embs, rows, q_rec, cand_rec, topk: int = 0):
         """Rerank merged global candidates: the label/KG tables are replicated, the candidate

@@ -1,5 +1,6 @@
-"""2-GPU (NCCL) check of the sharded path: per-rank shard search + all-gather + on-device merge
-+ sharded rerank == the single-GPU result.  Skipped unless two GPUs are visible."""
+"""Multi-GPU check of the sharded path (world 2 / 4 / 8, whatever is visible): per-rank shard search, the
+NVLink peer-memory exchange with the fused merge + rerank kernel, the NCCL all-gather transport, the serving
+loop -- all equal to the single-GPU result, bit for bit; a missing peer is reported after the timeout."""
 import os
 import socket
 
@@ -32,9 +33,10 @@ def _worker(rank, world, port, out_dir):
     qd = torch.from_numpy(q).cuda()
     rows, scores = s.search(qd, k)
     q_rec = torch.arange(n, n + b, device="cuda")
-    order, sc = s.rerank(rer, qd, rows, q_rec, rows.clone(), topk=20)
-    rows2, scores2, order2, sc2 = s.search_rerank(rer, qd, k, q_rec, topk=20)       # one-collective path
-    want_ids, want_fin = torch.gather(rows, 1, order.long()), sc[:, :, 0]
+    order, sc = s.rerank(rer, qd, rows, q_rec, rows.clone(), topk=20)                 # recomputed cosines, all-reduced
+    rows2, scores2, order2, sc2 = s.search_rerank(rer, qd, k, q_rec, topk=20)       # one-collective path (search scores)
+    assert torch.equal(rows2, rows) and torch.equal(scores2, scores)
+    want_ids, want_fin = torch.gather(rows2, 1, order2.long()), sc2[:, :, 0].contiguous()
     # query-split post-processing over NVLink peer memory (csrc/exchange.cu): several rounds so that
     # both buffer parities are used, then other batch sizes / K (ragged last slice, re-created region)
     for _ in range(3):
@@ -42,11 +44,10 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         assert getattr(s, "_px", None) is not None, "peer exchange was not used"
         assert torch.equal(ids3, want_ids) and torch.equal(fin3, want_fin)
+    s._px.check()
     s_nccl = ShardedSearcher(eng, use_peer=False)                                     # same step through NCCL
     ids4, fin4 = s_nccl.retrieve_reranked(rer, qd, k, q_rec, topk=20)
     torch.cuda.synchronize()
-    assert torch.equal(rows2, rows) and torch.equal(scores2, scores)
-    assert torch.equal(order2, order) and torch.equal(sc2, sc)
     assert torch.equal(ids4, want_ids) and torch.equal(fin4, want_fin)
     # serving loop (pipelined copies) == direct calls, on every rank
     batches = [torch.from_numpy(osr.to_bf16_round(synth.make_embeddings(b, d, seed=60 + i))).pin_memory() for i in range(4)]
@@ -56,35 +57,61 @@ def _worker(rank, world, port, out_dir):
         w_ids, w_fin = s_nccl.retrieve_reranked(rer, hb.cuda(), k, q_rec, topk=20)
         torch.cuda.synchronize()
         assert torch.equal(g_ids, w_ids.cpu()) and torch.equal(g_fin, w_fin.cpu())
-    for bb, kk in ((33, 50), (1, 10), (70, 64)):
+    for bb, kk in ((33, 50), (1, 10), (70, 64), (5, 128)):
         a_ids, a_fin = s.retrieve_reranked(rer, qd[:bb].contiguous(), kk, q_rec[:bb].contiguous(), topk=0)
         b_ids, b_fin = s_nccl.retrieve_reranked(rer, qd[:bb].contiguous(), kk, q_rec[:bb].contiguous(), topk=0)
         torch.cuda.synchronize()
         assert torch.equal(a_ids, b_ids) and torch.equal(a_fin, b_fin), (bb, kk)
+    # K beyond the fused kernels: the searcher falls back to the all-gather transport by itself
+    f_ids, f_fin = s.retrieve_reranked(rer, qd[:9].contiguous(), 200, q_rec[:9].contiguous(), topk=0)
+    g_ids, g_fin = s_nccl.retrieve_reranked(rer, qd[:9].contiguous(), 200, q_rec[:9].contiguous(), topk=0)
+    torch.cuda.synchronize()
+    assert torch.equal(f_ids, g_ids) and torch.equal(f_fin, g_fin)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), rows=rows.cpu().numpy(), scores=scores.cpu().numpy(),
-             order=order.cpu().numpy(), sc=sc.cpu().numpy())
+             order=order.cpu().numpy(), sc=sc.cpu().numpy(), ids=ids3.cpu().numpy(), fin=fin3.cpu().numpy())
     if rank == 0:  # single-shard reference on the same device
         full = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
         r1, s1 = full.search(qd, k)
         o1, c1 = rer.rerank_device(full, qd, r1, q_rec, r1.clone(), topk=20)
+        i1, f1 = rer.rerank_scored_device(r1, s1, q_rec, topk=20)
         np.savez(os.path.join(out_dir, "single.npz"), rows=r1.cpu().numpy(), scores=s1.cpu().numpy(),
-                 order=o1.cpu().numpy(), sc=c1.cpu().numpy())
+                 order=o1.cpu().numpy(), sc=c1.cpu().numpy(), ids=i1.cpu().numpy(), fin=f1.cpu().numpy())
     dist.barrier()
+    # a rank that never shows up: the others give up after the timeout and report it (no hung GPU)
+    s2 = ShardedSearcher(eng)
+    s2.retrieve_reranked(rer, qd, k, q_rec, topk=20)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        from multi_modal_retrieval_predict_project_b200 import _lib
+        _lib.check(_lib.load().mmr_exchange_set_timeout(s2._px._h, 300))
+        s2.retrieve_reranked(rer, qd, k, q_rec, topk=20)            # rank 0 alone runs a step
+        torch.cuda.synchronize()
+        try:
+            s2._px.check()
+            raise AssertionError("the missing peer was not reported")
+        except _lib.MMRError as e:
+            assert "timed out" in str(e)
+    dist.barrier()
+    s2.close(); s.close()
     dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_equals_single(tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_sharded_equals_single(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     single = np.load(tmp_path / "single.npz")
-    for rank in range(2):
+    for rank in range(world):
         z = np.load(tmp_path / f"r{rank}.npz")
         assert np.array_equal(z["rows"], single["rows"]) and np.array_equal(z["scores"], single["scores"])
         assert np.array_equal(z["order"], single["order"]) and np.allclose(z["sc"], single["sc"], rtol=0, atol=1e-12)
+        # the sharded step (NVLink exchange, fused merge + rerank) == the single-GPU fused tail, bit for bit
+        assert np.array_equal(z["ids"], single["ids"]) and np.array_equal(z["fin"], single["fin"])
 
 
 def test_serve_loop_single_gpu():

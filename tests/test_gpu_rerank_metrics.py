@@ -117,6 +117,131 @@ def test_batched_device_rerank_vs_oracle():
         assert np.all(np.abs(final[order[i]][mism] - final[want][mism]) < 1e-5)
 
 
+def _tables(n, b, d_kg, seed, p=0.1):
+    rng = np.random.default_rng(seed)
+    bits = (rng.random((n + b, 43)) < p)
+    masks = (bits.astype(np.uint64) << np.arange(43, dtype=np.uint64)).sum(axis=1).astype(np.uint64)
+    kg = rng.standard_normal((n + b, d_kg)).astype(np.float32)
+    kg = kg / (np.linalg.norm(kg, axis=1, keepdims=True) + 1e-12)
+    kg[7] = 0.0                                   # a record without a KG vector
+    return masks, kg
+
+
+@pytest.mark.parametrize("n,d,b,k,topk,d_kg", [(5000, 256, 40, 100, 20, 300), (3000, 128, 70, 10, 0, 48),
+                                               (60, 64, 5, 100, 0, 300), (2000, 64, 9, 128, 128, 512)])
+def test_fused_tail_vs_oracle_and_unfused_kernels(n, d, b, k, topk, d_kg):
+    """mmr_rerank_scored (one kernel: features + min-max + combine + order, embedding feature = the search
+    score): (a) against the oracle restatement of Reranker.rerank's scoring (reranker.py:298-329) fed the
+    candidates' stored embeddings -- the oracle recomputes safe_cos, the kernel reuses the search score, same
+    quantity; (b) bit-identical to the unfused kernels (rerank_features with the same cosines -> combine ->
+    apply_order); (c) K > N: padded candidates are excluded from the min-max and come out as id -1."""
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, _lib, synth
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=5, clustered=True))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=6, clustered=True))
+    masks, kg = _tables(n, b, d_kg, 7)
+    w = (0.4, 0.2, 0.2)
+    eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
+    rer = Reranker.from_tables(masks, kg, alpha=w[0], beta=w[1], gamma=w[2], device=0)
+    assert rer.fused_tail_ok(k)
+    qd = torch.from_numpy(q).cuda()
+    q_rec = torch.arange(n, n + b, device="cuda")
+    rows, scores = eng.search(qd, k)
+    ids, fin, s4 = rer.rerank_scored_device(rows, scores, q_rec, topk, want_scores4=True)
+    keep = topk if 0 < topk < k else k
+    valid = min(k, n)
+    rows_h, ids_h, fin_h = rows.cpu().numpy(), ids.cpu().numpy(), fin.cpu().numpy()
+    for i in range(b):
+        cand = rows_h[i, :valid]
+        want = orr.rerank_from_arrays(q[i], g[cand], masks[n + i], masks[cand], kg[n + i], kg[cand], *w, topk=keep)
+        ok, why = orr.reranked_lists_match(ids_h[i, :min(keep, valid)], fin_h[i, :min(keep, valid)], cand, want)
+        assert ok, (i, why)
+        assert np.all(ids_h[i, valid:] == -1) and np.all(fin_h[i, valid:] == 0.0)
+    # (b) the unfused kernels given the same cosines
+    if valid == k:
+        order, sc = rer.rerank_with_cos_device(scores, q_rec, rows, topk)
+        ids2 = torch.empty_like(ids); fin2 = torch.empty_like(fin)
+        lib = _lib.load()
+        _lib.check(lib.mmr_apply_order(_lib.ptr(rows), _lib.ptr(order), _lib.ptr(sc), b, k, keep, _lib.ptr(ids2),
+                                       _lib.ptr(fin2), 0, _lib.current_stream(0)))
+        torch.cuda.synchronize()
+        assert torch.equal(ids, ids2) and torch.equal(fin, fin2) and torch.equal(s4, sc)
+    # host buffers through the raw C ABI
+    lib = _lib.load()
+    o_ids = np.empty((b, keep), np.int64); o_fin = np.empty((b, keep), np.float64)
+    scores_h, q_rec_h = scores.cpu().numpy(), q_rec.cpu().numpy()
+    st = lib.mmr_rerank_scored(rer._tables, rows_h.ctypes.data, scores_h.ctypes.data, q_rec_h.ctypes.data, b, k,
+                               w[0], w[1], w[2], topk, o_ids.ctypes.data, o_fin.ctypes.data, None, 0, None)
+    assert st == 0, lib.mmr_last_error()
+    assert np.array_equal(o_ids, ids_h) and np.array_equal(o_fin, fin_h)
+    assert lib.mmr_rerank_scored(rer._tables, rows_h.ctypes.data, scores_h.ctypes.data, None, b, 200,
+                                 w[0], w[1], w[2], 0, o_ids.ctypes.data, o_fin.ctypes.data, None, 0, None) == _lib.MMR_EUNSUP
+
+
+def test_exchange_kernels_on_one_gpu_equal_the_single_shard_path():
+    """The fused exchange (mmr_search_scatter: selection kernel storing into the owner's region;
+    mmr_exchange_rerank: wait + merge + rerank + publish in one kernel) with world = 1, driven through the raw
+    C ABI: same (ids, scores) as search -> mmr_rerank_scored, over several steps (both buffer parities) and a
+    ragged K (padding of the lists to a multiple of 4).  Also: size / state errors, abort, and a (b, k)
+    mismatch is reported instead of hanging."""
+    import ctypes as C
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, _lib, synth
+    n, d, b = 30000, 128, 300
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=25))
+    masks, kg = _tables(n, b, 300, 27)
+    eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
+    rer = Reranker.from_tables(masks, kg, device=0)
+    lib = _lib.load()
+    ex = C.c_void_p()
+    _lib.check(lib.mmr_exchange_create(C.byref(ex), 0, 1, b, 100, 0))
+    q_rec = torch.arange(n, n + b, device="cuda")
+    step = 0
+    for k, bb, topk, algo in ((100, 300, 0, "gemm"), (10, 300, 5, "gemm"), (50, 37, 0, "gemm"), (7, 3, 0, "scan"),
+                              (100, 2, 30, "scan")):
+        qd = torch.from_numpy(osr.to_bf16_round(synth.make_embeddings(bb, d, seed=30 + step))).cuda()
+        rows, scores = eng.search(qd, k, algo=algo)
+        want_ids, want_fin = rer.rerank_scored_device(rows, scores, q_rec[:bb].contiguous(), topk)
+        for _ in range(2):
+            step += 1
+            _lib.check(lib.mmr_search_scatter(eng._handle, ex, _lib.ptr(qd), bb, _lib.MMR_F32, k, _lib.ALGOS[algo], step,
+                                              _lib.current_stream(0)))
+            p_ids, p_fin = C.c_void_p(), C.c_void_p()
+            _lib.check(lib.mmr_exchange_rerank(ex, rer._tables, _lib.ptr(q_rec), bb, k, rer.alpha, rer.beta, rer.gamma,
+                                               topk, step, C.byref(p_ids), C.byref(p_fin), _lib.current_stream(0)))
+            keep = topk if 0 < topk < k else k
+            ids = _lib.as_cuda_tensor(p_ids.value, (bb, keep), torch.int64, 0)
+            fin = _lib.as_cuda_tensor(p_fin.value, (bb, keep), torch.float64, 0)
+            torch.cuda.synchronize()
+            assert torch.equal(ids, want_ids) and torch.equal(fin, want_fin), (k, bb, topk, algo)
+    code = C.c_int32(-1)
+    assert lib.mmr_exchange_status(ex, C.byref(code)) == 0 and code.value == 0
+    assert lib.mmr_search_scatter(eng._handle, ex, _lib.ptr(qd), 301, _lib.MMR_F32, 10, 0, step + 1, None) == _lib.MMR_EINVAL
+    assert lib.mmr_exchange_create(C.byref(C.c_void_p()), 0, 1, 10, 129, 0) == _lib.MMR_EUNSUP
+    # a rerank whose (b, k) differs from what was scattered: reported, not hung
+    step += 1
+    _lib.check(lib.mmr_search_scatter(eng._handle, ex, _lib.ptr(qd), 2, _lib.MMR_F32, 100, 0, step, _lib.current_stream(0)))
+    p_ids, p_fin = C.c_void_p(), C.c_void_p()
+    _lib.check(lib.mmr_exchange_rerank(ex, rer._tables, _lib.ptr(q_rec), 2, 50, 0.6, 0.25, 0.15, 0, step, C.byref(p_ids),
+                                       C.byref(p_fin), _lib.current_stream(0)))
+    torch.cuda.synchronize()
+    assert lib.mmr_exchange_status(ex, C.byref(code)) == _lib.MMR_ECUDA and code.value == 3
+    assert b"different batch size or k" in lib.mmr_last_error()
+    assert lib.mmr_search_scatter(eng._handle, ex, _lib.ptr(qd), 2, _lib.MMR_F32, 100, 0, step + 1, None) == _lib.MMR_ECUDA
+    _lib.check(lib.mmr_exchange_destroy(ex))
+    # a wait for a step nobody scattered gives up after the timeout (and at once after an abort)
+    ex2 = C.c_void_p()
+    _lib.check(lib.mmr_exchange_create(C.byref(ex2), 0, 1, 8, 10, 0))
+    _lib.check(lib.mmr_exchange_set_timeout(ex2, 150))
+    _lib.check(lib.mmr_exchange_rerank(ex2, rer._tables, _lib.ptr(q_rec), 4, 10, 0.6, 0.25, 0.15, 0, 1, C.byref(p_ids),
+                                       C.byref(p_fin), _lib.current_stream(0)))
+    torch.cuda.synchronize()
+    assert lib.mmr_exchange_status(ex2, C.byref(code)) == _lib.MMR_ECUDA and code.value in (1, 2)
+    assert torch.all(_lib.as_cuda_tensor(p_ids.value, (4, 10), torch.int64, 0) == -1)
+    _lib.check(lib.mmr_exchange_abort(ex2))
+    _lib.check(lib.mmr_exchange_destroy(ex2))
+
+
 def test_metrics_match_reference_golden_bit_for_bit():
     from multi_modal_retrieval_predict_project_b200.Helpers import retrieval_metrics as m
     gold = json.load(open(GOLDEN / "metrics.json"))
