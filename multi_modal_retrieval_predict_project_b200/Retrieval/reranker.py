@@ -337,17 +337,19 @@ class Reranker:
                                                       _lib.current_stream(self.device)))
         return out
 
-    def rerank_with_cos_device(self, emb_cos, q_rec, cand_rec, topk: int = 0):
+    def rerank_with_cos_device(self, emb_cos, q_rec, cand_rec, topk: int = 0, counts=None):
         """Rerank with the embedding cosines supplied (sharded path): label Jaccard + KG cosine from
-        the replicated tables, then the same min-max / combine / ordering."""
+        the replicated tables, then the same min-max / combine / ordering.  ``counts`` (B) int32: valid
+        candidates per query (default K everywhere)."""
         import torch
         b, k = emb_cos.shape
         keep = topk if 0 < topk < k else k
         order = torch.empty((b, keep), dtype=torch.int32, device=emb_cos.device)
         sc = torch.empty((b, keep, 4), dtype=torch.float64, device=emb_cos.device)
+        emb_cos, q_rec, cand_rec = emb_cos.contiguous(), q_rec.contiguous(), cand_rec.contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.mmr_rerank_with_cos(self._tables, _lib.ptr(emb_cos), _lib.ptr(q_rec),
-                                                     _lib.ptr(cand_rec), None, b, k, self.alpha, self.beta,
+                                                     _lib.ptr(cand_rec), _lib.ptr(counts), b, k, self.alpha, self.beta,
                                                      self.gamma, int(topk), _lib.ptr(order), _lib.ptr(sc),
                                                      self.device, _lib.current_stream(self.device)))
         return order, sc

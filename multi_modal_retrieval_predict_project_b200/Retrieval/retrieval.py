@@ -325,17 +325,32 @@ class B200RetrievalEngine(RetrievalEngine):
         qids = [query_id] if (single or not isinstance(query_id, (list, tuple))) else list(query_id)
         if len(qids) != b:
             qids = (qids * b)[:b]
-        out_ids, out_scores = [], []
+        out_ids, out_scores, local = [], [], []
         for i in range(b):
             valid = rows[i] >= 0
             r = rows[i][valid] - self.row_offset
-            ids = [self.ids[int(j)] for j in r]
-            sc = [float(s) for s in scores[i][valid]]
-            if reranker is not None and qids[i] is not None:
+            local.append(r)
+            out_ids.append([self.ids[int(j)] for j in r])
+            out_scores.append([float(s) for s in scores[i][valid]])
+        todo = [i for i in range(b) if reranker is not None and qids[i] is not None]
+        if todo and hasattr(reranker, "rerank_rows"):
+            # ONE device call for the whole batch (the reference loops over queries in Python)
+            qh = q.detach().float().cpu().numpy() if _is_tensor(q) else q
+            kmax = max(len(local[i]) for i in todo)
+            cand = -np.ones((len(todo), kmax), dtype=np.int64)
+            q_embs = np.empty((len(todo), self.dim), dtype=np.float32)
+            for t, i in enumerate(todo):
+                cand[t, : len(local[i])] = local[i] + self.row_offset
+                # the STORED gallery row replaces q when query_id is a gallery id (reference retrieval.py:251-254)
+                q_embs[t] = self.get_embeddings_for_ids([qids[i]])[0] if str(qids[i]) in self.id2idx else qh[i]
+            res = reranker.rerank_rows(self, [qids[i] for i in todo], q_embs, cand, [out_ids[i] for i in todo],
+                                       rerank_topk or K)
+            for t, i in enumerate(todo):
+                out_ids[i], out_scores[i] = [x[0] for x in res[t]], [x[1] for x in res[t]]
+        else:
+            for i in todo:
                 qv = q[i].detach().float().cpu().numpy() if _is_tensor(q) else q[i]
-                ids, sc = self._rerank(reranker, qids[i], qv, ids, r, rerank_topk or K)
-            out_ids.append(ids)
-            out_scores.append(sc)
+                out_ids[i], out_scores[i] = self._rerank(reranker, qids[i], qv, out_ids[i], local[i], rerank_topk or K)
         if single:
             return out_ids[0], out_scores[0]
         return out_ids, out_scores
@@ -434,6 +449,140 @@ class B200RetrievalEngine(RetrievalEngine):
         return graph
 
 
+class MultiGPURetrievalEngine(RetrievalEngine):
+    """The reference's single-process engine interface over SEVERAL GPUs of one box:
+    ``make_retrieval_engine(fp, ip, method="b200", devices=[0, 1, ...])``.  The gallery is split into
+    contiguous row shards, one ``B200RetrievalEngine`` per device; ``retrieve`` keeps
+    the reference signature (string ids, ``reranker=``, ``query_id=``; ``Retrieval/retrieval.py:140-151``):
+    every shard is searched on its own device and stream (the launches overlap), the per-shard lists are
+    copied to the first device and merged there (``mmr_merge_topk``), and for a rerank every shard evaluates the
+    fp32 cosine of the candidates IT owns (``mmr_candidate_cosine``), which the first device sums and feeds to
+    the label / KG rerank.  A device may be listed more than once (several shards on one GPU)."""
+
+    def __init__(self, features_path: Optional[str] = None, ids_path: Optional[str] = None, *, devices: Sequence[int],
+                 dtype: str = "float32", algo: str = "auto", embs=None, ids=None, **_ignored):
+        if features_path is not None:
+            super().__init__(features_path, ids_path)
+        else:
+            self.embs = np.ascontiguousarray(embs, dtype=np.float32)
+            self.ids = list(ids) if ids is not None else _VirtualIds(len(self.embs))
+            self.id2idx = ({str(self.ids[i]): i for i in range(len(self.ids))} if ids is not None
+                           else _VirtualId2Idx(self.ids))
+        if not devices:
+            raise ValueError("devices must name at least one GPU")
+        from ..sharded import shard_bounds
+        self.devices = [_lib.require_cuda(d) for d in devices]
+        self.n, self.dim = int(self.embs.shape[0]), int(self.embs.shape[1])
+        self.row_offset = 0
+        self.dtype = "bfloat16" if _DTYPES[dtype] == _lib.MMR_BF16 else "float32"
+        self.shards: List[B200RetrievalEngine] = []
+        for r, dev in enumerate(self.devices):
+            lo, hi = shard_bounds(self.n, len(self.devices), r)
+            self.shards.append(B200RetrievalEngine.from_arrays(self.embs[lo:hi], dtype=dtype, device=dev, algo=algo,
+                                                               row_offset=lo, keep_host=False))
+        self.device = self.devices[0]
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        self.shards = []
+
+    def search(self, queries, K: int):
+        """Exact global top-K of a batch: ``(rows (B, K) int64, scores (B, K) fp32)`` CUDA tensors on the
+        first device, best first, -1 / -inf padding when the gallery has fewer than K rows."""
+        import torch
+        from ..sharded import merge_topk
+        q = queries.detach().float() if _is_tensor(queries) else torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32))
+        if q.dim() == 1:
+            q = q.unsqueeze(0)
+        if int(q.shape[1]) != self.dim:
+            raise ValueError(f"query dimension {q.shape[1]} != gallery dimension {self.dim}")
+        parts = []
+        for s in self.shards:                                    # asynchronous on every device
+            with torch.cuda.device(s.device):
+                qd = q.to(torch.device("cuda", s.device), non_blocking=True)
+                parts.append(s.search(qd, K))
+        dev0 = torch.device("cuda", self.device)
+        for s in self.shards:
+            torch.cuda.current_stream(s.device).synchronize()   # peer copies below read the shards' results
+        rows = torch.stack([r.to(dev0) for r, _ in parts])
+        scores = torch.stack([sc.to(dev0) for _, sc in parts])
+        if len(parts) == 1:
+            return rows[0], scores[0]
+        with torch.cuda.device(self.device):
+            return merge_topk(scores, rows, K)
+
+    def _candidate_cosines(self, q_embs: np.ndarray, cand_rows: np.ndarray):
+        """(B, K) fp32 cosine(q, stored row) of candidates given by GLOBAL row, each evaluated by the shard that
+        owns the row (safe_cos, reranker.py:135-142); -1 rows give 0.  Returns a CUDA tensor on the first device."""
+        import torch
+        b, k = cand_rows.shape
+        dev0 = torch.device("cuda", self.device)
+        total = torch.zeros((b, k), dtype=torch.float32, device=dev0)
+        outs = []
+        for s in self.shards:
+            with torch.cuda.device(s.device):
+                d = torch.device("cuda", s.device)
+                qd = torch.from_numpy(q_embs).to(d)
+                rd = torch.from_numpy(cand_rows).to(d)
+                out = torch.empty((b, k), dtype=torch.float32, device=d)
+                _lib.check(s._lib.mmr_candidate_cosine(s._handle, _lib.ptr(qd), _lib.ptr(rd), b, k, self.dim,
+                                                       _lib.ptr(out), None, _lib.current_stream(s.device)))
+                outs.append((out, qd, rd))
+        for (out, _qd, _rd), s in zip(outs, self.shards):
+            torch.cuda.current_stream(s.device).synchronize()
+            total += out.to(dev0)
+        return total
+
+    def retrieve(self, query_emb, K: int = 5, seed_size: int = 5, max_steps: int = 100,
+                 candidate_multiplier: int = 10, reranker=None, query_id=None,
+                 rerank_topk: Optional[int] = None, seed: Optional[int] = None):
+        """Signature and return types of ``DLSRetrievalEngine.retrieve`` (reference ``retrieval.py:140-151``);
+        see ``B200RetrievalEngine.retrieve``."""
+        import torch
+        q = query_emb.detach().float().cpu().numpy() if _is_tensor(query_emb) else np.asarray(query_emb, dtype=np.float32)
+        single = q.ndim == 1 or q.shape[0] == 1
+        q = np.ascontiguousarray(q.reshape(1, -1) if q.ndim == 1 else q, dtype=np.float32)
+        rows_d, scores_d = self.search(q, K)
+        rows, scores = rows_d.cpu().numpy(), scores_d.cpu().numpy()
+        b = rows.shape[0]
+        qids = [query_id] if (single or not isinstance(query_id, (list, tuple))) else list(query_id)
+        if len(qids) != b:
+            qids = (qids * b)[:b]
+        out_ids = [[self.ids[int(j)] for j in rows[i][rows[i] >= 0]] for i in range(b)]
+        out_scores = [[float(x) for x in scores[i][rows[i] >= 0]] for i in range(b)]
+        todo = [i for i in range(b) if reranker is not None and qids[i] is not None]
+        if todo:
+            if not hasattr(reranker, "rerank_with_cos_device"):
+                raise TypeError("the multi-GPU engine reranks with the B200 Reranker (device tables)")
+            if reranker.device != self.device:
+                raise ValueError("the Reranker's tables must live on the engine's first device")
+            kmax = max(len(out_ids[i]) for i in todo)
+            cand = -np.ones((len(todo), kmax), dtype=np.int64)
+            crec = -np.ones((len(todo), kmax), dtype=np.int64)
+            q_embs = np.empty((len(todo), self.dim), dtype=np.float32)
+            counts = np.zeros(len(todo), dtype=np.int32)
+            for t, i in enumerate(todo):
+                n_i = len(out_ids[i])
+                counts[t] = n_i
+                cand[t, :n_i] = rows[i][:n_i]
+                crec[t, :n_i] = reranker._rec_rows(out_ids[i])
+                q_embs[t] = self.get_embeddings_for_ids([qids[i]])[0] if str(qids[i]) in self.id2idx else q[i]
+            cos = self._candidate_cosines(q_embs, cand)
+            dev0 = torch.device("cuda", self.device)
+            keep = rerank_topk or K
+            order, sc = reranker.rerank_with_cos_device(cos, torch.from_numpy(reranker._rec_rows([qids[i] for i in todo])).to(dev0),
+                                                        torch.from_numpy(crec).to(dev0), keep,
+                                                        counts=torch.from_numpy(counts).to(dev0))
+            order, sc = order.cpu().numpy(), sc.cpu().numpy()
+            for t, i in enumerate(todo):
+                sel = [(int(j), float(s4[0])) for j, s4 in zip(order[t], sc[t]) if j >= 0]
+                out_ids[i], out_scores[i] = [out_ids[i][j] for j, _ in sel], [f for _, f in sel]
+        if single:
+            return out_ids[0], out_scores[0]
+        return out_ids, out_scores
+
+
 def make_retrieval_engine(features_path: str, ids_path: str, method: str = "dls", **kwargs) -> RetrievalEngine:
     """Factory with the reference's signature (``retrieval.py:273-304``).
 
@@ -442,13 +591,17 @@ def make_retrieval_engine(features_path: str, ids_path: str, method: str = "dls"
     reference accepts -- also returns the exact engine: it is a strict improvement on the walk
     (every DLS result is drawn from the exact ranking) and its kwargs ``link_threshold``,
     ``max_links``, ``fdb_path``, ``name`` are accepted and ignored.  Anything else raises
-    ``ValueError`` like the reference.
+    ``ValueError`` like the reference.  ``devices=[0, 1, ...]`` row-shards the gallery over several GPUs of
+    the box behind the same ``retrieve`` signature (``MultiGPURetrievalEngine``).
     """
     method = method.lower()
-    if method in ("b200", "exact", "cuda", "dls"):
-        return B200RetrievalEngine(features_path, ids_path, **kwargs)
+    kwargs = dict(kwargs)
     if method in ("bf16", "b200-bf16"):
-        kwargs = dict(kwargs)
         kwargs["dtype"] = "bfloat16"
+        method = "b200"
+    if method in ("b200", "exact", "cuda", "dls"):
+        devices = kwargs.pop("devices", None)
+        if devices is not None and len(devices) > 0:        # row-sharded over several GPUs, same interface
+            return MultiGPURetrievalEngine(features_path, ids_path, devices=list(devices), **kwargs)
         return B200RetrievalEngine(features_path, ids_path, **kwargs)
     raise ValueError(f"Unknown retrieval method: {method}")

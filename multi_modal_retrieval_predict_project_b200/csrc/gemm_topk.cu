@@ -80,6 +80,15 @@ constexpr int kTrack = 8;                         // per-thread running top-8 us
 #define MMR_EPI_SPLIT 1
 #endif
 constexpr bool kSplit = MMR_EPI_SPLIT != 0;
+// Append path.  1: the chunk's scaled scores are NOT kept in registers; the warp ORs its lanes' masks of hit
+// column groups (one REDUX) and, for every hit group, re-reads those 4 accumulator columns from TMEM (the stage is
+// still ours), rescales and appends -- straight-line code in a loop over the hit groups (typically one), and the
+// tracker update is predicated instead of branched.  0: the round-1 form (32 scaled scores live, eight
+// vote + branch pairs per chunk) for A/B builds.  The append path runs for ~40 % of the chunks of a short launch.
+#ifndef MMR_SLOW_RELOAD
+#define MMR_SLOW_RELOAD 1
+#endif
+constexpr bool kReload = MMR_SLOW_RELOAD != 0;
 constexpr int kEpiCols = kSplit ? kBlockN / kEpiGroups : kBlockN;   // accumulator columns a warpgroup drains per tile
 constexpr int kEpiStep = kSplit ? 1 : kEpiGroups;                    // tile stride of a warpgroup
 
@@ -179,6 +188,27 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrivals that hand a TMEM stage back to the MMA issuer order nothing but tcgen05 accesses (tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync precede them): relaxed, so that the arriving thread does not sit in a
+// memory fence waiting for its warp's outstanding candidate-list stores (L2 write round trips) on the critical
+// path of the stage release.
+#ifndef MMR_RELAXED_ARRIVE
+#define MMR_RELAXED_ARRIVE 1
+#endif
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+#if MMR_RELAXED_ARRIVE
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  mbar_arrive_cluster(cluster_addr);
+#endif
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+#if MMR_RELAXED_ARRIVE
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+#else
+  mbar_arrive_n(bar, 1);
+#endif
+}
 // TMA load into THIS CTA's shared memory whose completion bytes are credited to a barrier that may
 // live in the peer CTA (`bar_cluster` is a shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* smem, int c0,
@@ -253,6 +283,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -647,6 +682,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const float qinv = q_ok ? q_inv[q] : 0.f;
     uint2* const buf = cand + (static_cast<int64_t>(q_ok ? q : 0) * n_lists + list) * cap;
     uint32_t cnt = 0;                                // append cursor: entries in this thread's list
+#ifdef MMR_GEMM_TRACE
+    uint32_t dbg_chunks = 0, dbg_slow = 0, dbg_groups = 0;
+#endif
     float tau_local = q_ok ? -INFINITY : INFINITY;   // pre-threshold from this list's own k-th best (strict)
     float tau_pre = tau_local;                       // effective conservative threshold on acc * inv_norm(g)
     // running top-8 of the best-of-chunk final scores this thread has appended (a subset of its list,
@@ -818,8 +856,56 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           continue;
         }
 #endif
+#ifdef MMR_GEMM_TRACE
+        ++dbg_chunks;
+#endif
         if (__any_sync(0xffffffffu, m > tau_pre)) {  // warp-uniform
           const uint32_t colbase = static_cast<uint32_t>(n0) + static_cast<uint32_t>(c * 32);
+#ifdef MMR_GEMM_TRACE
+          ++dbg_slow;
+#endif
+          if (kReload) {
+            uint32_t hm = 0u;  // this lane's groups of 4 columns with a hit
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) hm |= (gm[j4] > tau_pre) ? (1u << j4) : 0u;
+            uint32_t um = __reduce_or_sync(0xffffffffu, hm);
+            if (debug_flags & 32) um = 0u;
+            while (um != 0u) {  // typically one group
+#ifdef MMR_GEMM_TRACE
+              ++dbg_groups;
+#endif
+              const uint32_t j4 = static_cast<uint32_t>(__ffs(um) - 1);
+              um &= um - 1u;
+              uint32_t a4[4];
+              tmem_ld4(taddr + static_cast<uint32_t>(c * 32) + j4 * 4u, a4);
+              float g0, g1, g2, g3;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(g3)
+                           : "r"(ginv_s + (static_cast<uint32_t>(c * 32) + j4 * 4u) * 4u));
+              tmem_ld_wait();
+              const uint32_t col = colbase + j4 * 4u;
+              score_step(buf, cnt, __uint_as_float(a4[0]) * g0, tau_pre, qinv, col + 0u);
+              score_step(buf, cnt, __uint_as_float(a4[1]) * g1, tau_pre, qinv, col + 1u);
+              score_step(buf, cnt, __uint_as_float(a4[2]) * g2, tau_pre, qinv, col + 2u);
+              score_step(buf, cnt, __uint_as_float(a4[3]) * g3, tau_pre, qinv, col + 3u);
+            }
+            // m was appended above: fold it into the running top-8 (a no-op unless it beats the smallest slot;
+            // predicated with -inf instead of branched) and publish when the r-th best moved
+            if (track && (debug_flags & 64) == 0) {
+              float x = (m > tau_pre) ? m * qinv : -INFINITY;
+#pragma unroll
+              for (int i = 0; i < kTrack; ++i) {
+                const float hi = fmaxf(top[i], x);
+                x = fminf(top[i], x);
+                top[i] = hi;
+              }
+              const float rth = top[kTrack - 1];
+              if (rth > published) {
+                published = rth;
+                __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
+              }
+            }
+          } else {
           // second-level filter: only the groups of 4 columns in which some lane has a hit run the
           // predicated append (typically 1-3 of 8)
 #pragma unroll
@@ -846,6 +932,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               published = rth;
               __stcg(tau_pub + static_cast<int64_t>(list) * b_pad + q, f32_to_ordered(rth));
             }
+          }
           }
           // make room for the next 32 columns: compact every list of this warp that is nearly full
           uint32_t need = (debug_flags & 128) ? 0u : __ballot_sync(0xffffffffu, cnt > full_cnt);
@@ -874,9 +961,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // all 4 warps are done with TMEM stage + ginv
       if (epi_tid == 0) {  // the MMA issuer (the leader CTA's in pair mode) may overwrite this stage
         if (kPair)
-          mbar_arrive_cluster(mapa_rank(smem_u32(&aux->tmem_empty[acc]), 0u));
+          mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&aux->tmem_empty[acc]), 0u));
         else
-          mbar_arrive_n(&aux->tmem_empty[acc], 1);
+          mbar_arrive_relaxed(&aux->tmem_empty[acc]);
       }
     }
 #ifdef MMR_GEMM_TRACE
@@ -937,6 +1024,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       trace[static_cast<size_t>(blockIdx.x) * 64 + 62] = now;
+      // slots 58-61: chunks drained by this warp, chunks that took the append path, hit groups, entries lane 0 appended
+      trace[static_cast<size_t>(blockIdx.x) * 64 + 58] = dbg_chunks;
+      trace[static_cast<size_t>(blockIdx.x) * 64 + 59] = dbg_slow;
+      trace[static_cast<size_t>(blockIdx.x) * 64 + 60] = dbg_groups;
+      trace[static_cast<size_t>(blockIdx.x) * 64 + 61] = cnt;
     }
 #endif
   }

@@ -75,3 +75,6 @@ for name, sel in (("wave 1", ~wave2), ("wave 2", wave2)):
     print("   last tile drained ", stat(rel(63)[sel]), "  (since entry:", stat(rel(63)[sel] - e[sel]), ")")
     print("   final pass done   ", stat(rel(62)[sel]), "  (final pass:", stat(rel(62)[sel] - rel(63)[sel]), ")")
 print("kernel span from the trace (us):", round(float(rel(62).max()), 1))
+ch, sl, gr, ap = (t[:, c].astype(np.float64) for c in (58, 59, 60, 61))
+print("append path (warp 0 of warpgroup 0 of every CTA): chunks %.0f, took the append path %.1f %%, hit groups per such chunk %.2f, "
+      "entries appended by lane 0: %.0f" % (ch.mean(), 100.0 * sl.sum() / max(ch.sum(), 1), gr.sum() / max(sl.sum(), 1), ap.mean()))

@@ -11,5 +11,5 @@ run() {  # lib debug rows trace?
 }
 for lib in ${LIBS:-libmmr_b200_diag.so libmmr_b200_diag_nosplit.so}; do
   echo "=== $lib"
-  for d in ${DEBUGS:-0}; do run $lib $d ${ROWS:-1250000}; done
+  for d in ${DEBUGS:-0}; do run $lib $d ${ROWS:-1250000} ${TRACE:-}; done
 done

@@ -85,6 +85,45 @@ def test_engine_retrieve_with_reranker_vs_oracle(tmp_path):
                         [(i, s, 0, 0, 0) for i, s in zip(ids, scores)], **TOL)
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_multi_device_engine_reference_signature(tmp_path, dtype):
+    """make_retrieval_engine(fp, ip, method="b200", devices=[...]).retrieve(q, K, reranker=, query_id=) -- the
+    reference signature (string ids, Retrieval/retrieval.py:140-151) over row shards on several devices -- returns
+    what the single-GPU engine returns, with and without a rerank, for gallery-id and external query ids, single
+    and batched queries.  Uses every visible GPU; on a one-GPU box the shards share the device (three shards on
+    device 0: same code path, same merge and cross-shard cosine sum)."""
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import MultiGPURetrievalEngine, Reranker, make_retrieval_engine
+    a = build_rerank_artifacts(str(tmp_path))
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
+    one = make_retrieval_engine(a["features_path"], a["ids_path"], method="b200", dtype=dtype, device=0)
+    many = make_retrieval_engine(a["features_path"], a["ids_path"], method="b200", dtype=dtype, devices=devices)
+    assert isinstance(many, MultiGPURetrievalEngine) and len(many.shards) == len(devices)
+    assert many.ids == one.ids and np.array_equal(many.get_embeddings_for_ids(["g3", "zz"]), one.get_embeddings_for_ids(["g3", "zz"]))
+    rer = Reranker(a["kg_dir"], a["csv"], device=0)
+    # bf16: both engines run the same (vectorised) feature kernel => identical; fp32: the single engine's gather
+    # kernel and the cross-shard path's KG kernel sum in different orders (1e-8 on the combined score)
+    atol = 1e-12 if dtype == "bfloat16" else 1e-7
+    for q, qid in ((a["qs"][0], a["qids"][0]), (a["qs"][1].reshape(1, -1), "g17"), (a["g"][5], "g5")):
+        assert many.retrieve(q, K=7) == one.retrieve(q, K=7)
+        ids_m, sc_m = many.retrieve(q, K=20, reranker=rer, query_id=qid, rerank_topk=8)
+        ids_1, sc_1 = one.retrieve(q, K=20, reranker=rer, query_id=qid, rerank_topk=8)
+        assert ids_m == ids_1 and len(ids_m) == 8 and np.allclose(sc_m, sc_1, rtol=0, atol=atol)
+        assert all(isinstance(x, str) for x in ids_m) and all(isinstance(x, float) for x in sc_m)
+    nested_m = many.retrieve(a["qs"][:5], K=10, reranker=rer, query_id=list(a["qids"][:5]))
+    nested_1 = one.retrieve(a["qs"][:5], K=10, reranker=rer, query_id=list(a["qids"][:5]))
+    assert nested_m[0] == nested_1[0] and np.allclose(np.array(nested_m[1]), np.array(nested_1[1]), rtol=0, atol=atol)
+    assert len(many.retrieve(a["qs"][0], K=1000)[0]) == len(a["ids"])              # K > N -> N results
+    # the batched result equals the per-query one (one device call for the whole batch)
+    for i in range(5):
+        ids_i, sc_i = one.retrieve(a["qs"][i], K=10, reranker=rer, query_id=a["qids"][i])
+        assert ids_i == nested_1[0][i] and sc_i == nested_1[1][i]
+    with pytest.raises(ValueError):
+        many.search(np.zeros((1, 3), np.float32), 3)
+    many.close(); one.close(); rer.close()
+
+
 def test_batched_device_rerank_vs_oracle():
     import torch
     from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, synth
