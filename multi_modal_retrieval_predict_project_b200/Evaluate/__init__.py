@@ -70,7 +70,13 @@ def compute_ranking_metrics(query_embs, gallery_embs, query_labels, gallery_labe
         _lib.check(lib.mmr_first_relevant_rank(eng._handle, _lib.ptr(q), nq, _lib.MMR_F32, _lib.ptr(qm), _lib.ptr(gm),
                                                qm.shape[1], _lib.ptr(rank), _lib.ptr(total),
                                                _lib.current_stream(eng.device)))
-    kk = min(int(k), n, _lib.MAX_K)
+    if min(int(k), n) > _lib.MAX_K:
+        eng.close()
+        # (the reference accepts any k; the search kernels keep at most MMR_MAX_K candidates per query, and a
+        # Recall@k computed over a shorter list would be silently wrong)
+        raise NotImplementedError(f"compute_ranking_metrics: k = {k} exceeds the {_lib.MAX_K} results the search "
+                                  "kernels return per query")
+    kk = min(int(k), n)
     rows, _ = eng.search(q, kk)
     eng.close()
     valid = rows >= 0                                              # relevance of the k retrieved rows

@@ -25,17 +25,22 @@ class Reranker:
 
     Extra (keyword-only) arguments over the reference: ``device``, ``label_attention`` (path to a
     ``label_attention_model.pt`` checkpoint; the reference looks for it under its own BASE_DIR,
-    ``reranker.py:62-63``) and ``la_hidden_dim`` (``configs/config.yaml:47``).
+    ``reranker.py:62-63``) and ``la_hidden_dim`` (``configs/config.yaml:47``).  ``preload_record_kg`` is accepted
+    for signature compatibility: the record KG table is always built up front here (it IS the device table; fp32,
+    the reference's optional precomputed table is fp64 -- the cosines are evaluated in fp32 either way).
     """
 
     def __init__(self, kg_dir: Optional[Path] = None, labels_csv: Optional[Path] = None, alpha: float = 0.6,
                  beta: float = 0.25, gamma: float = 0.15, preload_record_kg: bool = True, *, device=None,
                  label_attention: Optional[Path] = None, la_hidden_dim: int = 256):
-        if kg_dir is None or labels_csv is None:
-            raise FileNotFoundError("Reranker needs kg_dir and labels_csv (the reference's defaults point into "
-                                    "its own checkout: knowledge_graph/ and outputs/openi_labels_final.csv)")
-        self.kg_dir = Path(kg_dir)
-        self.labels_csv = Path(labels_csv)
+        # the reference's defaults are relative to its checkout (reranker.py:11-15: BASE_DIR / "knowledge_graph",
+        # BASE_DIR / "outputs" / "openi_labels_final.csv"); here BASE_DIR = $MMR_B200_BASE_DIR or the working
+        # directory (the reference's scripts are run from the repository root).  Missing files raise
+        # FileNotFoundError exactly like the reference (:103, :116, pandas for the CSV).
+        import os
+        base = Path(os.environ.get("MMR_B200_BASE_DIR", os.getcwd()))
+        self.kg_dir = Path(kg_dir) if kg_dir else base / "knowledge_graph"
+        self.labels_csv = Path(labels_csv) if labels_csv else base / "outputs" / "openi_labels_final.csv"
         self.alpha, self.beta, self.gamma = alpha, beta, gamma
         self.kg = self._load_kg(self.kg_dir)
         self.labels_df = pd.read_csv(self.labels_csv, index_col="id")

@@ -44,6 +44,7 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         assert getattr(s, "_px", None) is not None, "peer exchange was not used"
         assert torch.equal(ids3, want_ids) and torch.equal(fin3, want_fin)
+    ids3, fin3 = ids3.clone(), fin3.clone()      # views of the exchange region: it is re-created below (larger K)
     s._px.check()
     s_nccl = ShardedSearcher(eng, use_peer=False)                                     # same step through NCCL
     ids4, fin4 = s_nccl.retrieve_reranked(rer, qd, k, q_rec, topk=20)

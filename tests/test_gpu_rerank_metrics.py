@@ -53,6 +53,23 @@ def test_rerank_errors_match_reference(tmp_path):
         rer.rerank("t0", ["g1", "g2"], candidate_embs=a["g"][:2])
     with pytest.raises(FileNotFoundError):
         Reranker(str(tmp_path / "missing"), a["csv"], device=0)
+    # the reference's default arguments resolve relative to its checkout (reranker.py:11-15, 38-39); here relative
+    # to $MMR_B200_BASE_DIR / the working directory: missing files raise like the reference, present ones load
+    import os
+    import shutil
+    with pytest.raises(FileNotFoundError, match="node2id.json"):
+        Reranker(device=0)
+    base = tmp_path / "checkout"
+    shutil.copytree(a["kg_dir"], base / "knowledge_graph")
+    os.makedirs(base / "outputs")
+    shutil.copy(a["csv"], base / "outputs" / "openi_labels_final.csv")
+    os.environ["MMR_B200_BASE_DIR"] = str(base)
+    try:
+        r0 = Reranker(device=0)
+        assert r0.get_record_label_set("g0") == rer.get_record_label_set("g0")
+        r0.close()
+    finally:
+        del os.environ["MMR_B200_BASE_DIR"]
     # label sets / kg vectors agree with the oracle's python-loop versions
     ora = orr.OracleReranker(a["kg_dir"], a["csv"])
     for rid in ["g0", "g5", "g6", "g13", "t2", "t3", "zzz"]:
@@ -122,6 +139,35 @@ def test_multi_device_engine_reference_signature(tmp_path, dtype):
     with pytest.raises(ValueError):
         many.search(np.zeros((1, 3), np.float32), 3)
     many.close(); one.close(); rer.close()
+
+
+def test_rerank_tie_order_is_candidate_position_ascending():
+    """Exact ties in the combined score (the rule of the reference's own la_only variant: alpha = 0, beta = 1,
+    gamma = 0 -- discrete Jaccard values) come out in ASCENDING candidate position, in the unfused kernels and
+    in the fused tail alike.  The reference's np.argsort(final)[::-1] (reranker.py:327) leaves tie order to
+    numpy's unstable sort (for <= 16 candidates it happens to be descending position); INTEGRATION.md
+    documents the deterministic rule as a deliberate divergence."""
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import Reranker
+    n, k = 64, 24
+    masks = np.zeros(n + 1, dtype=np.uint64)
+    masks[:n] = np.array([0b0011, 0b0110, 0b0011, 0b1000], dtype=np.uint64)[np.arange(n) % 4]
+    masks[n] = 0b0011                                            # the query's labels
+    kg = np.zeros((n + 1, 8), dtype=np.float32)
+    rer = Reranker.from_tables(masks, kg, alpha=0.0, beta=1.0, gamma=0.0, device=0)
+    rows = torch.arange(k, device="cuda").flip(0).reshape(1, k).contiguous()          # candidates 23, 22, ..., 0
+    scores = torch.linspace(0.9, 0.1, k, device="cuda").reshape(1, k).contiguous()
+    q_rec = torch.tensor([n], device="cuda")
+    ids, fin, s4 = rer.rerank_scored_device(rows, scores, q_rec, 0, want_scores4=True)
+    order, sc = rer.rerank_with_cos_device(scores, q_rec, rows, 0)
+    torch.cuda.synchronize()
+    fin_h, ids_h = fin.cpu().numpy()[0], ids.cpu().numpy()[0]
+    assert np.all(np.diff(fin_h) <= 0) and set(np.unique(fin_h)) == {0.0, 1.0 / 3.0, 1.0}
+    pos = {int(r): j for j, r in enumerate(rows.cpu().numpy()[0])}                  # candidate position of every id
+    for v in np.unique(fin_h):
+        tied = [pos[int(i)] for i in ids_h[fin_h == v]]
+        assert tied == sorted(tied) and len(tied) > 1
+    assert np.array_equal(order.cpu().numpy()[0], [pos[int(i)] for i in ids_h]) and torch.equal(sc, s4)
 
 
 def test_batched_device_rerank_vs_oracle():
@@ -381,6 +427,17 @@ def test_diversity_matches_reference_golden():
         e = np.array(c["emb"], dtype=np.float32).reshape(len(c["emb"]), -1) if c["emb"] else np.zeros((0, 4), np.float32)
         assert np.isclose(compute_embedding_diversity(e), c["emb_div"], rtol=0, atol=2e-6)
         assert compute_label_diversity_from_labels(c["labels"]) == c["label_div"]
+
+
+def test_compute_ranking_metrics_rejects_k_beyond_the_kernel_limit():
+    """k > MMR_MAX_K on a gallery larger than that used to compute Recall@k over the top 1024 only (ADVICE)."""
+    from multi_modal_retrieval_predict_project_b200.Evaluate import compute_ranking_metrics
+    rng = np.random.default_rng(0)
+    g = rng.standard_normal((1500, 16)).astype(np.float32)
+    lab = (rng.random((1500, 8)) < 0.2).astype(np.int64)
+    with pytest.raises(NotImplementedError, match="exceeds"):
+        compute_ranking_metrics(g[:4], g, lab[:4], lab, k=1200)
+    compute_ranking_metrics(g[:4], g[:900], lab[:4], lab[:900], k=1200)      # k > N <= limit is fine
 
 
 def test_compute_ranking_metrics_large_gallery_vs_oracle():
