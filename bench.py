@@ -439,13 +439,16 @@ def main():
             got += 1                                     # rank 0: res = host (ids, scores) of one step
         assert got == n
 
+    e2e_kern = None
     if reranker is not None:
         e2e_run(2)                                       # untimed warm-up of the copy path
         barrier()
+        engine.profile(True)
         t0 = time.perf_counter()
         e2e_run(args.steps)
         barrier()
         e2e_s = time.perf_counter() - t0
+        e2e_kern = engine.profile(False)
     else:
         out_host = [torch.empty(shp, dtype=dt).pin_memory() for shp, dt in out_shapes]
         qd = torch.empty_like(q_dev)
@@ -470,6 +473,8 @@ def main():
     d2h = sum(int(np.prod(shp)) * torch.empty((), dtype=dt).element_size() for shp, dt in out_shapes)
     e2e = {"value": b * args.steps / max_over_ranks(e2e_s), "unit": UNIT,
            "h2d_bytes_per_step": q_host.numel() * q_host.element_size(), "d2h_bytes_per_step": d2h}
+    if e2e_kern is not None and e2e_kern[1] > 0:
+        e2e["search_kernel_ms"] = e2e_kern[0] / e2e_kern[1]      # the dominant kernel inside the serving loop
 
     # ---------------- roofline of the dominant kernel (which one: asked from the library) --------
     n_local = hi - lo

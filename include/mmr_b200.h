@@ -62,9 +62,9 @@ extern "C" {
 #define MMR_TUNE_GEMM_VARIANT 0  /* value: MMR_GEMM_VARIANT_* */
 #define MMR_TUNE_GEMM_PARTS   1  /* value: 0 = automatic, > 0 = number of gallery parts per query tile */
 #define MMR_TUNE_GEMM_PAIR    2  /* value: MMR_GEMM_PAIR_* */
-#define MMR_GEMM_VARIANT_AUTO  0 /* short-launch variant for <= 2048 gallery tiles per part, else long-launch */
-#define MMR_GEMM_VARIANT_LONG  1 /* long-launch instantiation: lists fill and compact, lockstep start-up */
-#define MMR_GEMM_VARIANT_SHORT 2 /* short-launch instantiation: probe pass + pacing + bound-filtered final pass */
+#define MMR_GEMM_VARIANT_AUTO  0 /* = SHORT whenever every candidate list of the launch gets a full gallery tile */
+#define MMR_GEMM_VARIANT_LONG  1 /* lists fill and compact, lockstep start-up, no pacing (round-1 form for long launches) */
+#define MMR_GEMM_VARIANT_SHORT 2 /* probe pass on the first tile + paced sharers + bound-filtered final pass */
 #define MMR_GEMM_PAIR_AUTO 0     /* cta_group::2 CTA pairs whenever the batch has >= 2 query tiles */
 #define MMR_GEMM_PAIR_OFF  1     /* single-CTA (cta_group::1) instantiation */
 

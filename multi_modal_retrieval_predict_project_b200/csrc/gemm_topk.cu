@@ -30,9 +30,10 @@
 // across lists, every list publishes the score of its r-th best, r = ceil(k / n_lists): if every
 // list holds >= r candidates >= g = min over lists, the union holds >= k, so nothing below g can be
 // in the global top-k and all CTAs of the query tile prune with g.  select.cu merges the lists.
-// Short launches run the kProbe instantiation: a probe pass over the first tile seeds g before anything is
-// appended, the leaders pace themselves on the slowest sharer of their gallery part, and the final per-list
-// pass filters by g before any exact selection (see the comments at those sites and DESIGN.md section 4).
+// The default (kProbe) instantiation: a probe pass over the first tile seeds g before anything is appended, the
+// leaders pace themselves on the slowest sharer of their gallery part, and the final per-list pass filters by
+// g before any exact selection (see the comments at those sites and DESIGN.md section 4); kProbe = false is
+// the round-1 "long launch" form, kept selectable (mmr_index_tune) and parity-tested.
 //
 // Roofline: tensor-core bound, 2 * b * n * d_pad FLOP per launch.
 #include <cuda.h>
@@ -570,7 +571,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // index and holds its loads while the slowest sharer of its part is more than pace_w tiles
         // behind.  Advisory only: a sharer that makes no progress for ~100 us (not resident yet) switches
         // pacing off for this unit; finished units publish "done".
-        uint32_t* const progress = (kProbe && tau_pub != nullptr && pace_w > 0 && leader)
+        uint32_t* const progress = (tau_pub != nullptr && pace_w > 0 && leader)
                                        ? tau_pub + static_cast<size_t>(m_tiles) * kBlockM * (n_parts * kEpiGroups)
                                        : nullptr;
         const int n_share = min(m_group, m_units - (unit / per_group) * m_group);
@@ -579,7 +580,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < num_tiles; ++t) {
-          if (kProbe && pace_live && (t & 7) == 0) {
+          if (pace_live && (t & 7) == 0) {
             *reinterpret_cast<volatile uint32_t*>(progress + unit) = static_cast<uint32_t>(t) + 1u;
             if (t >= pace_w) {
               for (int spins = 0;; ++spins) {
@@ -623,7 +624,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           }
         }
-        if (kProbe && progress != nullptr) *reinterpret_cast<volatile uint32_t*>(progress + unit) = 0xFFFFFFFFu;  // done
+        if (progress != nullptr) *reinterpret_cast<volatile uint32_t*>(progress + unit) = 0xFFFFFFFFu;  // done
       }
     } else if (warp == kMmaWarp) {
       // ===================== MMA issuer =====================
@@ -1146,15 +1147,18 @@ int plan_gemm(int64_t n, int d_pad, int b, int k, int num_sms, const GemmTune& t
   }
   plan->tiles_per_part = tiles_per_part;
   plan->cap = cap;
-  // Short launches (<= 2048 tiles per part: the shards at N >= 4, cfg2, cfg5) run the kProbe kernel:
-  // the ~300 us per-wave warm-up it removes is 10-25 % of such a launch.  Long launches keep the original
-  // start-up: its lockstep compactions keep the sharers of a gallery part aligned for the whole launch
-  // (ncu at 10M x 4096: L2 hit 78 % / 28.8 GB of DRAM reads, vs 68 % / 36.2 GB with probe + pacing)
-  // and the warm-up is < 2 % there.  mmr_index_tune(MMR_TUNE_GEMM_VARIANT) pins either instantiation.
+  // Which instantiation.  AUTO = the kProbe kernel (probe pass on the first tile, pacing of the sharers of a
+  // gallery part, bound-filtered final pass) whenever every list of the launch gets at least one full tile.
+  // Round 1 kept the other instantiation ("long": lists fill and compact, the sharers stay aligned through their
+  // synchronous first compactions) for launches of more than 2048 tiles per part, because the probe variant with
+  // its 64-tile pacing window re-read the gallery more (36 vs 29 GB at 10M rows).  With a 12-tile window the
+  // kProbe kernel reads 24.5 GB there (the long one 41 GB since its epilogue got faster and its sharers drift)
+  // and is 6 % faster in the power-capped bench loop (29.7 vs 32.5 ms; isolated 26.3 vs 27.6 ms, tensor pipe
+  // 96.6 % active).  mmr_index_tune(MMR_TUNE_GEMM_VARIANT) pins either instantiation (tests, A/B runs).
   {
-    int probe_max = 2048;
+    int probe_max = 0x7FFFFFFF;
 #ifdef MMR_DIAG
-    static const int probe_max_env = diag_env("MMR_B200_GEMM_PROBE_MAX_TILES", 2048);
+    static const int probe_max_env = diag_env("MMR_B200_GEMM_PROBE_MAX_TILES", 0x7FFFFFFF);
     probe_max = probe_max_env;
 #endif
     const int tiles_last = static_cast<int>(tiles_total) - (n_parts - 1) * tiles_per_part;
@@ -1201,7 +1205,13 @@ int launch_gemm_topk(const void* emb_bf16, const float* inv_norm, int64_t n, int
   // 1M x 2048/4096 (16 sharers): without the synchronous first compaction the sharers drift apart
   // and the part is re-read from HBM ~5x (ncu: dram read 1.18 -> 5.36 GB).
   int early_tiles = plan.m_group * (pair ? 2 : 1) <= 8 ? 8 : 0;
-  int pace_w = 64;  // only read by the kProbe kernel
+  // Pacing window (tiles a leader may run ahead of the slowest sharer of its gallery part; 0 = off).  The sharers
+  // of a part share it through L2 only while they stay within the part's share of the 126 MB: measured (ncu DRAM
+  // bytes + bench-loop time, scripts/exp_pace.sh) 12 tiles is best from ~1000 tiles per part up (2.5M rows: 5.7 vs
+  // 14.0 GB read; 5M: 14.5 vs 15.3 ms; 10M: 29.7 vs 31.8 ms), while launches of a few hundred tiles per part, which
+  // run at full clocks with no power cap, lose 4 % to a tight window (1.25M rows: 3.51 ms at 64, 3.66 at 16).
+  // The long-launch instantiation relies on its lockstep start-up and is not paced.
+  int pace_w = plan.probe ? (plan.tiles_per_part <= 768 ? 64 : 12) : 0;
   int flags = 0;    // diagnostic builds: bit 0 skips the score processing, bit 1 the probe pass
 #ifdef MMR_DIAG
   // MMR_B200_GEMM_DEBUG bit 0: skip the epilogue's score processing (results are garbage) to measure the

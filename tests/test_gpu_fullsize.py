@@ -38,14 +38,14 @@ def _headline_queries(b=4096):
     return torch.randn((b, DIM), generator=gq, device="cuda").to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize("variant", ["auto", "short"])
+@pytest.mark.parametrize("variant", ["auto", "long"])
 def test_headline_shape_vs_bruteforce_oracle(big, variant):
-    """The launch bench.py times at N = 1 -- 10M x 512 bf16, b = 4096, k = 100, AUTO dispatch = the long-launch
-    CTA-pair instantiation gemm_topk_kernel<resident, pair, kProbe=0> (9 parts x 4341 tiles) -- compared
-    with the oracle for 64 queries spread over all 32 query tiles: ids position by position outside
-    near-ties and scores to 2e-5 against the fp32 brute force over the same bf16 values
-    (oracle.search.topk_matches), exact recall@100 against the fp64 ranking with the epsilon rule.
-    The short-launch instantiation is forced on the same launch as well."""
+    """The launch bench.py times at N = 1 -- 10M x 512 bf16, b = 4096, k = 100, AUTO dispatch = the CTA-pair
+    instantiation gemm_topk_kernel<resident, pair, kProbe=1> on 9 parts x 4341 tiles -- compared with the
+    oracle for 64 queries spread over all 32 query tiles: ids position by position outside near-ties and
+    scores to 2e-5 against the fp32 brute force over the same bf16 values (oracle.search.topk_matches), exact
+    recall@100 against the fp64 ranking with the epsilon rule.  The other instantiation (kProbe=0, round 1's
+    choice for this launch) is forced on the same launch as well."""
     from oracle.bruteforce import check_topk
     eng, g = big["eng"], big["g"]
     q = _headline_queries()
@@ -54,7 +54,7 @@ def test_headline_shape_vs_bruteforce_oracle(big, variant):
     plan = eng.last_plan()
     eng.tune(variant="auto")
     assert plan["algo"] == "gemm" and plan["pair"] and plan["parts"] == 9 and plan["tiles_per_part"] == 4341, plan
-    assert plan["variant"] == ("long" if variant == "auto" else "short"), plan
+    assert plan["variant"] == ("short" if variant == "auto" else "long"), plan
     sel = torch.arange(0, 4096, 64, device="cuda") + torch.arange(64, device="cuda") % 64   # one per 64, all lanes
     ok, detail = check_topk(rows[sel], scores[sel], g, q[sel], 100)
     assert ok, detail
@@ -67,15 +67,15 @@ def test_headline_shape_vs_bruteforce_oracle(big, variant):
 
 
 def test_shard_shape_n8_vs_bruteforce_oracle(big):
-    """The launch bench.py times at N = 8 (1.25M-row shard, b = 4096, k = 100): AUTO = the short-launch
-    instantiation <resident, pair, kProbe=1>; and the N = 2 shard (5M rows, long-launch).  64 sampled
-    queries each against the brute-force oracle over the same rows."""
+    """The launches bench.py times at N = 8 (1.25M-row shard, b = 4096, k = 100: 64-tile pacing window) and
+    at N = 2 (5M-row shard: 12-tile window), AUTO = <resident, pair, kProbe=1>.  64 sampled queries each
+    against the brute-force oracle over the same rows."""
     from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine
     from oracle.bruteforce import check_topk
     g = big["g"]
     q = _headline_queries()
     sel = torch.arange(0, 4096, 64, device="cuda") + torch.arange(64, device="cuda") % 64
-    for lo, hi, want in ((2_500_000, 3_750_000, "short"), (5_000_000, 10_000_000, "long")):
+    for lo, hi, want in ((2_500_000, 3_750_000, "short"), (5_000_000, 10_000_000, "short")):
         shard = B200RetrievalEngine.from_arrays(g[lo:hi], dtype="bfloat16", device=0, borrow=True, keep_host=False,
                                                 row_offset=lo)
         rows, scores = shard.search(q, 100)

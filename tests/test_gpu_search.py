@@ -272,6 +272,7 @@ def _tuned_search(eng, q, k, variant, parts, pair=True, min_tiles=200):
 @pytest.mark.parametrize("n,d,b,k,parts", [(120_000, 128, 300, 100, 2),    # 2 CTA pairs x 2 parts, odd tile count
                                            (150_001, 64, 100, 100, 1),     # single-CTA instantiation, ragged last tile
                                            (260_000, 512, 700, 100, 4),    # resident-Q pairs at d = 512, 3 pair units
+                                           (215_000, 64, 300, 100, 1),     # > 768 tiles per part: the 12-tile pacing window
                                            (110_000, 1024, 260, 10, 2)])   # streamed-Q pairs
 def test_gemm_variants_many_tiles_per_part(variant, n, d, b, k, parts):
     from multi_modal_retrieval_predict_project_b200 import synth

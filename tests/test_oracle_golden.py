@@ -231,3 +231,32 @@ def test_bruteforce_checker_is_pinned_on_the_numpy_oracle():
     assert ok, detail
     bad = r.copy(); bad[0, 0] = 1234 + 500
     assert not check_topk(bad, s, torch.from_numpy(g), torch.from_numpy(q), 10, row_offset=500)[0]
+
+
+def test_array_rerank_checker_is_pinned_on_the_file_based_oracle(tmp_path):
+    """oracle.rerank.rerank_from_arrays (the checker of bench.py's parity_check and of the fused-tail GPU tests:
+    integer label masks + KG rows instead of the CSV / node2id files) returns what OracleReranker.rerank --
+    itself pinned on the reference's golden vectors -- returns for the same records."""
+    from oracle import rerank as orr
+    from tests._fixtures import build_rerank_artifacts
+    a = build_rerank_artifacts(str(tmp_path))
+    ora = orr.OracleReranker(a["kg_dir"], a["csv"], 0.4, 0.2, 0.2)
+    all_ids = a["ids"] + a["qids"]
+    names = list(ora.labels_df.columns)
+    mask_of = {rid: sum(1 << names.index(c) for c in ora.get_record_label_set(rid)) for rid in all_ids}
+    kg_of = {rid: np.asarray(ora.get_record_kg_vec(rid), dtype=np.float32) for rid in all_ids}
+    rng = np.random.default_rng(3)
+    for qi in range(6):
+        cand = rng.choice(len(a["ids"]), size=40, replace=False)
+        cand_ids = [a["ids"][j] for j in cand]
+        qid = a["qids"][qi]
+        want = ora.rerank(qid, cand_ids, candidate_embs=a["g"][cand], query_emb=a["qs"][qi], topk=15)
+        got = orr.rerank_from_arrays(a["qs"][qi], a["g"][cand], mask_of[qid], [mask_of[c] for c in cand_ids], kg_of[qid],
+                                     [kg_of[c] for c in cand_ids], 0.4, 0.2, 0.2, topk=15)
+        assert [cand_ids[g_[0]] for g_ in got] == [w[0] for w in want]
+        assert np.allclose([g_[1:] for g_ in got], [w[1:] for w in want], rtol=0, atol=1e-6)
+        ok, why = orr.reranked_lists_match([cand[g_[0]] for g_ in got], [g_[1] for g_ in got], cand, got)
+        assert ok, why
+    bad = list(got)
+    bad[0], bad[5] = bad[5], bad[0]
+    assert not orr.reranked_lists_match([cand[g_[0]] for g_ in bad], [g_[1] for g_ in bad], cand, got)[0]
