@@ -31,8 +31,9 @@ struct KeySourceVar {  // GEMM candidates: (b, n_parts, cap) raw {score bits, lo
   const int64_t* exclude;  // optional (b) local row to drop per query
   __device__ __forceinline__ int64_t count(int) const { return static_cast<int64_t>(n_parts) * per_part; }
   __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
-    const int part = static_cast<int>(i / per_part);
-    const int j = static_cast<int>(i - static_cast<int64_t>(part) * per_part);
+    // n_parts * per_part < 2^31 (at most a few thousand lists of <= 1025 entries): 32-bit division
+    const int part = static_cast<int>(static_cast<uint32_t>(i) / static_cast<uint32_t>(per_part));
+    const int j = static_cast<int>(static_cast<uint32_t>(i) - static_cast<uint32_t>(part) * static_cast<uint32_t>(per_part));
     const int c = counts[static_cast<int64_t>(q) * n_parts + part];
     if (j >= (c < per_part ? c : per_part)) return 0ull;
     const uint2 e = cand[(static_cast<int64_t>(q) * n_parts + part) * cap + j];
@@ -310,10 +311,27 @@ select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, Sink 
       const uint64_t k0 = static_cast<int>(threadIdx.x) < m ? lvl2[threadIdx.x] : 0ull;
       const uint64_t k1 = static_cast<int>(threadIdx.x) + 256 < m ? lvl2[threadIdx.x + 256] : 0ull;
       int r0 = 0, r1 = 0;
-      for (int i = 0; i < m; ++i) {
-        const uint64_t kk = lvl2[i];
-        r0 += kk > k0 ? 1 : 0;
-        r1 += kk > k1 ? 1 : 0;
+      if ((m & 1) != 0 && threadIdx.x == 0) lvl2[m] = 0ull;   // pad to an even count (kRankCap < 8 * 128 slots)
+      __syncthreads();
+      // warps without a key skip the count; 16-byte shared loads (two keys, broadcast); the second key of a
+      // thread exists only when more than 256 candidates survived
+      if (warp * 32 < m) {
+        const ulonglong2* pairs = reinterpret_cast<const ulonglong2*>(lvl2);
+        const int np = (m + 1) >> 1;
+        if (m <= 256) {
+#pragma unroll 4
+          for (int i = 0; i < np; ++i) {
+            const ulonglong2 kk = pairs[i];
+            r0 += (kk.x > k0 ? 1 : 0) + (kk.y > k0 ? 1 : 0);
+          }
+        } else {
+#pragma unroll 2
+          for (int i = 0; i < np; ++i) {
+            const ulonglong2 kk = pairs[i];
+            r0 += (kk.x > k0 ? 1 : 0) + (kk.y > k0 ? 1 : 0);
+            r1 += (kk.x > k1 ? 1 : 0) + (kk.y > k1 ? 1 : 0);
+          }
+        }
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

@@ -222,7 +222,8 @@ class ShardedSearcher:
         order, sc = reranker.rerank_with_cos_device(cos, q_rec, out_r, topk)
         return out_r, out_s, order, sc
 
-    def retrieve_reranked(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None):
+    def retrieve_reranked(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None,
+                          buffers=None):
         """What ``retrieve(q, K, reranker=..., query_id=...)`` returns (Retrieval/retrieval.py:257-269)
         for a batch: ``(ids (B, keep) int64 in reranked order, combined scores (B, keep) fp64)``.  The record
         index of a candidate is its global row id; the rerank's embedding feature (reranker.py:298) is the
@@ -234,7 +235,10 @@ class ShardedSearcher:
         straight into the owner ranks' memory and one kernel per owner merges, reranks and publishes
         (csrc/exchange.cu); the returned tensors are views of this rank's exchange region, valid until the
         call after next.  Otherwise (``use_peer=False``, K > 128, fp32 index ...): one NCCL all-gather of the
-        per-rank blobs and two of the result slices."""
+        per-rank blobs and two of the result slices.
+
+        ``buffers`` (single shard, fused tail): a dict the call fills with / reuses ``rows``, ``scores``, ``ids``,
+        ``fin`` tensors, so that a serving loop allocates nothing per step."""
         import torch
         import torch.distributed as dist
         eng = self.engine
@@ -245,6 +249,15 @@ class ShardedSearcher:
         lib = _lib.load()
         by_score = getattr(reranker, "emb_feature", "search_score") == "search_score"
         if self.world == 1:
+            if buffers is not None and by_score and reranker.fused_tail_ok(K):
+                if "rows" not in buffers or tuple(buffers["rows"].shape) != (b, K) or tuple(buffers["ids"].shape) != (b, keep):
+                    buffers["rows"] = torch.empty((b, K), dtype=torch.int64, device=dev)
+                    buffers["scores"] = torch.empty((b, K), dtype=torch.float32, device=dev)
+                    buffers["ids"] = torch.empty((b, keep), dtype=torch.int64, device=dev)
+                    buffers["fin"] = torch.empty((b, keep), dtype=torch.float64, device=dev)
+                eng.search(queries, K, algo=algo, out_rows=buffers["rows"], out_scores=buffers["scores"])
+                return reranker.rerank_scored_device(buffers["rows"], buffers["scores"], q_rec, topk,
+                                                     out=(buffers["ids"], buffers["fin"]))
             rows, scores = eng.search(queries, K, algo=algo)
             if by_score and reranker.fused_tail_ok(K):
                 return reranker.rerank_scored_device(rows, scores, q_rec, topk)
@@ -318,7 +331,7 @@ class ShardedSearcher:
         dev = torch.device("cuda", self.engine.device)
         s_cmp = torch.cuda.current_stream(dev)
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        qd, hout = [None, None], [None, None]
+        qd, hout, bufs = [None, None], [None, None], [{}, {}]   # per-slot device buffers: nothing is allocated per step
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_cmp = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event(blocking=True) for _ in range(2)]
@@ -338,7 +351,9 @@ class ShardedSearcher:
                 qd[slot].copy_(batch, non_blocking=True)
                 ev_in[slot].record(s_in)
             s_cmp.wait_event(ev_in[slot])
-            ids, fin = self.retrieve_reranked(reranker, qd[slot], K, q_rec, topk=topk, algo=algo)
+            if i >= 2:
+                s_cmp.wait_event(ev_out[slot])         # the results of batch i - 2 have left bufs[slot]
+            ids, fin = self.retrieve_reranked(reranker, qd[slot], K, q_rec, topk=topk, algo=algo, buffers=bufs[slot])
             ev_cmp[slot].record(s_cmp)
             s_out.wait_event(ev_cmp[slot])
             if to_host:

@@ -3,6 +3,8 @@
 
     python profiles/summarize.py launches gpurun_out/launches_r1.csv  > profiles/r1_launches.md
     python profiles/summarize.py kernel  gpurun_out/prof_r1_gemm.ncu-rep gemm_topk > profiles/r1_gemm_topk.md
+    python profiles/summarize.py traffic gemm_topk_kernel:gpurun_out/prof_r2_gemm_long.ncu-rep:10000000:512:4096:100 \
+                                         scan_topk_kernel:gpurun_out/prof_r2_scan.ncu-rep:10000000:512:1:10 > profiles/traffic.json
 """
 import collections
 import csv
@@ -98,8 +100,30 @@ def kernel(rep, pat, top=25):
         print(f"| {s} | {100 * s / tot:.1f}% | {r[h['Instructions Executed']]} | `{r[h['Source']][:70]}` | {t[1]} |")
 
 
+def traffic(specs):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch per kernel -> the table bench.py reads
+    (roofline.traffic when the workload matches)."""
+    import json
+    out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures "
+                       "(profiles/summarize.py traffic); bench.py reports these as roofline.traffic when the workload matches"}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for spec in specs:
+        name, rep, rows, dim, batch, k = spec.split(":")
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rws = list(csv.reader(raw.splitlines()))
+        hdr, units = rws[0], rws[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        r = [x for x in rws[2:] if name.split("_kernel")[0] in x[idx['Kernel Name']]][0]
+        tot = sum(float(r[idx[m]].replace(',', '')) * mult[units[idx[m]]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        out[name] = {"rows": int(rows), "dim": int(dim), "batch": int(batch), "k": int(k), "bytes": int(tot),
+                     "kernel": r[idx['Kernel Name']][:80], "source": rep.split('/')[-1]}
+    print(json.dumps(out, indent=2))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
     else:
         kernel(sys.argv[2], sys.argv[3])
