@@ -34,9 +34,11 @@ struct KeySourceVar {  // GEMM candidates: (b, n_parts, cap) raw {score bits, lo
     // n_parts * per_part < 2^31 (at most a few thousand lists of <= 1025 entries): 32-bit division
     const int part = static_cast<int>(static_cast<uint32_t>(i) / static_cast<uint32_t>(per_part));
     const int j = static_cast<int>(static_cast<uint32_t>(i) - static_cast<uint32_t>(part) * static_cast<uint32_t>(per_part));
-    const int c = counts[static_cast<int64_t>(q) * n_parts + part];
+    // the entry is loaded whether or not it is valid (slots past the count are allocated, just stale): the
+    // count and the entry come back in ONE round trip instead of two dependent ones
+    const int c = __ldg(counts + static_cast<int64_t>(q) * n_parts + part);
+    const uint2 e = __ldcg(cand + (static_cast<int64_t>(q) * n_parts + part) * cap + j);
     if (j >= (c < per_part ? c : per_part)) return 0ull;
-    const uint2 e = cand[(static_cast<int64_t>(q) * n_parts + part) * cap + j];
     if (exclude != nullptr && static_cast<int64_t>(e.y) == exclude[q]) return 0ull;
     return make_key(__uint_as_float(e.x), e.y);
   }
@@ -257,7 +259,10 @@ struct RemoteSink {
 };
 
 template <typename Source, typename Bound, typename Sink>
-__global__ void __launch_bounds__(256)
+#ifndef MMR_SELECT_MIN_CTAS
+#define MMR_SELECT_MIN_CTAS 4   // 64 registers: four CTAs per SM (the kernel is a chain of L2 round trips)
+#endif
+__global__ void __launch_bounds__(256, MMR_SELECT_MIN_CTAS)
 select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, Sink sink, uint64_t* __restrict__ stage_keys) {
   __shared__ __align__(16) uint64_t lvl2[8 * 128];
   __shared__ int32_t lvl2_idx[8 * 128];
