@@ -193,7 +193,13 @@ exchange_rerank_kernel(RerankArgs a) {
       const int64_t row = a.l_rows[at];
       if (row >= 0) {
         const uint64_t key = make_key(a.l_scores[at], static_cast<uint32_t>(row));
-        if (static_cast<uint32_t>(key >> 32) >= bound) keys[atomicAdd(&s_m, 1)] = key;
+        if (static_cast<uint32_t>(key >> 32) >= bound) {
+          const int at_key = atomicAdd(&s_m, 1);
+#ifdef MMR_DIAG
+          if (at_key >= kMaxWorld * kTailMaxK) __trap();  // bounds-checked build
+#endif
+          keys[at_key] = key;
+        }
       }
     }
     __syncthreads();

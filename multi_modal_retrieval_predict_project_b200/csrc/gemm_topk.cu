@@ -936,6 +936,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
           }
           // make room for the next 32 columns: compact every list of this warp that is nearly full
+#ifdef MMR_DIAG
+          if (cnt > static_cast<uint32_t>(cap)) __trap();   // bounds-checked build: a list never outgrows its buffer
+#endif
           uint32_t need = (debug_flags & 128) ? 0u : __ballot_sync(0xffffffffu, cnt > full_cnt);
           while (need != 0u) {
             const int src = __ffs(need) - 1;

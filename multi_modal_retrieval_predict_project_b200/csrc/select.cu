@@ -34,6 +34,9 @@ struct KeySourceVar {  // GEMM candidates: (b, n_parts, cap) raw {score bits, lo
     // n_parts * per_part < 2^31 (at most a few thousand lists of <= 1025 entries): 32-bit division
     const int part = static_cast<int>(static_cast<uint32_t>(i) / static_cast<uint32_t>(per_part));
     const int j = static_cast<int>(static_cast<uint32_t>(i) - static_cast<uint32_t>(part) * static_cast<uint32_t>(per_part));
+#ifdef MMR_DIAG
+    if (part >= n_parts || j >= cap) __trap();  // bounds-checked build
+#endif
     // the entry is loaded whether or not it is valid (slots past the count are allocated, just stale): the
     // count and the entry come back in ONE round trip instead of two dependent ones
     const int c = __ldg(counts + static_cast<int64_t>(q) * n_parts + part);
@@ -251,6 +254,9 @@ struct RemoteSink {
   __device__ __forceinline__ void put(int q, int r, float score, int64_t row, int32_t) const {
     const int dest = q / s.per;
     const int64_t slot = (static_cast<int64_t>(s.my_rank) * s.per + (q - dest * s.per)) * s.kp + r;
+#ifdef MMR_DIAG
+    if (dest < 0 || dest >= kMaxWorld || s.peers.base[dest] == nullptr || r < 0 || r >= s.kp) __trap();  // bounds-checked build
+#endif
     reinterpret_cast<float*>(s.peers.base[dest] + s.off_scores)[slot] = score;
     reinterpret_cast<int64_t*>(s.peers.base[dest] + s.off_rows)[slot] = row;
   }

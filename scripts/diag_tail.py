@@ -1,5 +1,6 @@
 """Diagnostic (1 GPU): CUDA-event timing of the pieces of one search+rerank step after the GEMM:
-ingest of the queries, select, rerank features, rerank combine.  ROWS/BATCH from the environment."""
+ingest of the queries, select, rerank features, rerank combine -- and the fused tail kernel that replaces the
+last two on the batched path.  ROWS/BATCH from the environment."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -39,6 +40,8 @@ gemm_ms, gemm_n = eng.profile(False)
 t_rerank, _ = timed(lambda: rer.rerank_device(eng, q, r, q_rec, r, k))
 t_cos, cos = timed(lambda: rer.candidate_cosine_device(eng, q, r))
 t_rr_cos, _ = timed(lambda: rer.rerank_with_cos_device(cos, q_rec, r, k))
+t_fused, _ = timed(lambda: rer.rerank_scored_device(r, s, q_rec, k))          # the fused tail (mmr_rerank_scored)
 print({"rows": rows, "batch": b, "search_ms": round(t_search, 3), "gemm_ms": round(gemm_ms / gemm_n, 3),
        "ingest+select_ms": round(t_search - gemm_ms / gemm_n, 3), "rerank(features+combine)_ms": round(t_rerank, 3),
-       "candidate_cosine_ms": round(t_cos, 3), "rerank_with_cos_ms": round(t_rr_cos, 3)})
+       "candidate_cosine_ms": round(t_cos, 3), "rerank_with_cos_ms": round(t_rr_cos, 3),
+       "fused_tail_ms": round(t_fused, 3)})

@@ -1,6 +1,6 @@
 """Diagnostic (1 GPU): GEMM kernel time vs gallery rows at a fixed batch (CUDA events through
-mmr_index_profile).  MMR_B200_GEMM_DEBUG=1 disables the epilogue's score processing to expose the
-TMA + MMA pipeline alone."""
+mmr_index_profile).  With a -DMMR_DIAG build (MMR_B200_LIB=.../libmmr_b200_diag.so) MMR_B200_GEMM_DEBUG=1
+disables the epilogue's score processing to expose the TMA + MMA pipeline alone."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
