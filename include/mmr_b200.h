@@ -130,7 +130,8 @@ int mmr_search(mmr_index* index, const void* q, int32_t b, int32_t q_dtype, int3
  * (n_lists, b, k_in) list-major -- the layout all_gather_into_tensor produces -- with row = -1
  * padding allowed; outputs (b, k_out) best first.  out_src (may be NULL) receives for every
  * output slot the flat source position list*k_in + j (or -1), so that callers can carry
- * payload (rerank features) through the merge. */
+ * payload (rerank features) through the merge.  Row ids must be below 2^32 - 1 (the merge packs them into
+ * the low word of its ordering keys; mmr_index_create enforces the same bound on row_offset + n). */
 int mmr_merge_topk(const float* scores, const int64_t* rows, int32_t n_lists, int32_t b, int32_t k_in,
                    int32_t k_out, float* out_scores, int64_t* out_rows, int32_t* out_src,
                    int32_t device, void* stream);
