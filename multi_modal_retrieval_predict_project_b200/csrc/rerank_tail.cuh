@@ -17,6 +17,10 @@ namespace mmr {
 
 constexpr int kTailMaxK = 128;     // candidates per query the fused tail covers
 constexpr int kTailThreads = 256;
+#ifndef MMR_TAIL_CAND
+#define MMR_TAIL_CAND 2
+#endif
+constexpr int kTailCand = MMR_TAIL_CAND;   // candidates whose KG gathers a warp keeps in flight
 
 __device__ __forceinline__ float tail_safe_cos(float dot, float ssa, float ssb) {  // safe_cos, reranker.py:135-142
   const float na = sqrtf(ssa), nb = sqrtf(ssb);
@@ -62,12 +66,12 @@ __device__ __forceinline__ void rerank_tail(TailSmem& sm, int count, int64_t qr,
     qkss = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, qkss))));
   }
   qkss = warp_sum(qkss);
-  // ---- KG cosine: two candidates per warp in flight (all gathers issued before the first reduction) ----
-  for (int j0 = warp * 2; j0 < count; j0 += nwarps * 2) {
-    float4 y[2][kKIts];
-    bool do_kg[2];
+  // ---- KG cosine: kTailCand candidates per warp in flight (all gathers issued before the first reduction) ----
+  for (int j0 = warp * kTailCand; j0 < count; j0 += nwarps * kTailCand) {
+    float4 y[kTailCand][kKIts];
+    bool do_kg[kTailCand];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kTailCand; ++c) {
       const int j = j0 + c;
       const int64_t cr = j < count ? sm.cand_row[j] : -1;
       do_kg[c] = qkg != nullptr && cr >= 0 && cr < t.n_rec;
@@ -78,12 +82,14 @@ __device__ __forceinline__ void rerank_tail(TailSmem& sm, int count, int64_t qr,
         y[c][it] = (do_kg[c] && u < nk) ? __ldg(ck + u) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    float kdot[2] = {0.f, 0.f}, kss[2] = {0.f, 0.f};
+    float kdot[kTailCand], kss[kTailCand];
+#pragma unroll
+    for (int c = 0; c < kTailCand; ++c) kdot[c] = kss[c] = 0.f;
 #pragma unroll
     for (int it = 0; it < kKIts; ++it) {
       const float4 qa = *reinterpret_cast<const float4*>(sm.qks + (it * 32 + lane) * 4);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < kTailCand; ++c) {
         const float4 v = y[c][it];
         kdot[c] = fmaf(v.x, qa.x, fmaf(v.y, qa.y, fmaf(v.z, qa.z, fmaf(v.w, qa.w, kdot[c]))));
         kss[c] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, kss[c]))));
@@ -92,14 +98,14 @@ __device__ __forceinline__ void rerank_tail(TailSmem& sm, int count, int64_t qr,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < kTailCand; ++c) {
         kdot[c] += __shfl_xor_sync(0xffffffffu, kdot[c], o);
         kss[c] += __shfl_xor_sync(0xffffffffu, kss[c], o);
       }
     }
     if (lane == 0) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
+      for (int c = 0; c < kTailCand; ++c)
         if (j0 + c < count) sm.raw[2][j0 + c] = static_cast<double>(do_kg[c] ? tail_safe_cos(kdot[c], qkss, kss[c]) : 0.f);
     }
   }

@@ -233,35 +233,43 @@ constexpr int kRankCap = 512;
 // Where the selected (score, global row) pairs go: dense (b, k_out) arrays, or -- the fused select + scatter
 // of the sharded path -- straight into the exchange region of the rank that owns the query (16 x 4/8-byte
 // NVLink stores per query instead of a second kernel that re-reads the dense arrays).
+// The kernel stages a query's result (<= 128 slots) in shared memory and the sink flushes it with `nt` threads.
 struct DenseSink {
   float* scores;
   int64_t* rows;
   int32_t* src;
   int k_out;
   __device__ __forceinline__ int limit() const { return k_out; }
-  __device__ __forceinline__ void put(int q, int r, float score, int64_t row, int32_t from) const {
-    const int64_t o = static_cast<int64_t>(q) * k_out + r;
-    scores[o] = score;
-    rows[o] = row;
-    if (src != nullptr) src[o] = from;
+  __device__ __forceinline__ void flush(int q, const float* o_sc, const int64_t* o_row, const int32_t* o_src, int t,
+                                        int nt) const {
+    const int64_t base = static_cast<int64_t>(q) * k_out;
+    for (int i = t; i < k_out; i += nt) {
+      scores[base + i] = o_sc[i];
+      rows[base + i] = o_row[i];
+      if (src != nullptr) src[base + i] = o_src[i];
+    }
   }
-  __device__ __forceinline__ void pad(int q, int r) const { put(q, r, -INFINITY, -1, -1); }
-  __device__ __forceinline__ void finish() const {}
 };
 struct RemoteSink {
   PeerSink s;
   __device__ __forceinline__ int limit() const { return s.kp; }
-  __device__ __forceinline__ void put(int q, int r, float score, int64_t row, int32_t) const {
+  // 16-byte NVLink stores (kp is a multiple of 4 and the lists are 256-byte aligned in the region): 4- and 8-byte
+  // peer stores, one packet per element, made this kernel twice as slow as its dense form
+  __device__ __forceinline__ void flush(int q, const float* o_sc, const int64_t* o_row, const int32_t*, int t,
+                                        int nt) const {
     const int dest = q / s.per;
-    const int64_t slot = (static_cast<int64_t>(s.my_rank) * s.per + (q - dest * s.per)) * s.kp + r;
+    const int64_t slot = (static_cast<int64_t>(s.my_rank) * s.per + (q - dest * s.per)) * s.kp;
 #ifdef MMR_DIAG
-    if (dest < 0 || dest >= kMaxWorld || s.peers.base[dest] == nullptr || r < 0 || r >= s.kp) __trap();  // bounds-checked build
+    if (dest < 0 || dest >= kMaxWorld || s.peers.base[dest] == nullptr) __trap();  // bounds-checked build
 #endif
-    reinterpret_cast<float*>(s.peers.base[dest] + s.off_scores)[slot] = score;
-    reinterpret_cast<int64_t*>(s.peers.base[dest] + s.off_rows)[slot] = row;
+    float4* d_sc = reinterpret_cast<float4*>(s.peers.base[dest] + s.off_scores + slot * 4);
+    longlong2* d_row = reinterpret_cast<longlong2*>(s.peers.base[dest] + s.off_rows + slot * 8);
+    const float4* s_sc4 = reinterpret_cast<const float4*>(o_sc);
+    const longlong2* s_row2 = reinterpret_cast<const longlong2*>(o_row);
+    for (int v = t; v < s.kp / 4; v += nt) d_sc[v] = s_sc4[v];
+    for (int v = t; v < s.kp / 2; v += nt) d_row[v] = s_row2[v];
+    __threadfence_system();  // before the signal kernel's release
   }
-  __device__ __forceinline__ void pad(int q, int r) const { put(q, r, -INFINITY, -1, -1); }
-  __device__ __forceinline__ void finish() const { __threadfence_system(); }  // before the signal kernel's release
 };
 
 template <typename Source, typename Bound, typename Sink>
@@ -274,6 +282,9 @@ select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, Sink 
   __shared__ int32_t lvl2_idx[8 * 128];
   __shared__ __align__(16) uint64_t fin[128];
   __shared__ int32_t fin_idx[128];
+  __shared__ __align__(16) float o_sc[128];      // the query's result, staged for the sink's (vectorised) flush
+  __shared__ __align__(16) int64_t o_row[128];
+  __shared__ int32_t o_src[128];
   __shared__ int s_count;
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -348,12 +359,20 @@ select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, Sink 
       for (int h = 0; h < 2; ++h) {
         const uint64_t k64 = h == 0 ? k0 : k1;
         const int r = h == 0 ? r0 : r1;
-        if (k64 != 0ull && r < k_out)
-          sink.put(q, r, key_score(k64), row_offset + static_cast<int64_t>(key_row(k64)), lvl2_idx[threadIdx.x + h * 256]);
+        if (k64 != 0ull && r < k_out) {
+          o_sc[r] = key_score(k64);
+          o_row[r] = row_offset + static_cast<int64_t>(key_row(k64));
+          o_src[r] = lvl2_idx[threadIdx.x + h * 256];
+        }
       }
       // fewer candidates than k_out, and the sink's padding beyond k_out
-      for (int i = (m < k_out ? m : k_out) + threadIdx.x; i < sink.limit(); i += blockDim.x) sink.pad(q, i);
-      sink.finish();
+      for (int i = (m < k_out ? m : k_out) + threadIdx.x; i < sink.limit(); i += blockDim.x) {
+        o_sc[i] = -INFINITY;
+        o_row[i] = -1;
+        o_src[i] = -1;
+      }
+      __syncthreads();
+      sink.flush(q, o_sc, o_row, o_src, threadIdx.x, blockDim.x);
       return;
     }
     __syncthreads();  // lvl2 is reused below
@@ -384,26 +403,28 @@ select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, Sink 
     warp_bitonic_sort_desc_kv(fin, fin_idx, 128, lane);
     for (int i = lane; i < sink.limit(); i += 32) {
       const uint64_t k64 = (i < k_out) ? fin[i] : 0ull;
-      if (k64 == 0ull)
-        sink.pad(q, i);
-      else
-        sink.put(q, i, key_score(k64), row_offset + static_cast<int64_t>(key_row(k64)), fin_idx[i]);
+      o_sc[i] = k64 == 0ull ? -INFINITY : key_score(k64);
+      o_row[i] = k64 == 0ull ? -1 : row_offset + static_cast<int64_t>(key_row(k64));
+      o_src[i] = k64 == 0ull ? -1 : fin_idx[i];
     }
-    sink.finish();
+    __syncwarp();
+    sink.flush(q, o_sc, o_row, o_src, lane, 32);
   }
 }
 
 // dense (b, k) lists -> the owner ranks' regions (shapes the fused select + scatter does not cover)
 __global__ void scatter_lists_kernel(const float* __restrict__ scores, const int64_t* __restrict__ rows, int b, int k,
                                      RemoteSink sink) {
+  __shared__ __align__(16) float o_sc[MMR_MAX_K];
+  __shared__ __align__(16) int64_t o_row[MMR_MAX_K];
   const int q = blockIdx.x;
   for (int i = threadIdx.x; i < sink.limit(); i += blockDim.x) {
-    if (i < k && rows[static_cast<int64_t>(q) * k + i] >= 0)
-      sink.put(q, i, scores[static_cast<int64_t>(q) * k + i], rows[static_cast<int64_t>(q) * k + i], -1);
-    else
-      sink.pad(q, i);
+    const bool ok = i < k && rows[static_cast<int64_t>(q) * k + i] >= 0;
+    o_sc[i] = ok ? scores[static_cast<int64_t>(q) * k + i] : -INFINITY;
+    o_row[i] = ok ? rows[static_cast<int64_t>(q) * k + i] : -1;
   }
-  sink.finish();
+  __syncthreads();
+  sink.flush(q, o_sc, o_row, nullptr, threadIdx.x, blockDim.x);
 }
 
 // payload carried through a merge: out[q][i] = payload[list * stride + q * k_in + j] for the source
