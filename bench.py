@@ -433,10 +433,16 @@ def main():
         for _ in range(n):
             yield q_host                                 # this step's queries (pinned host memory)
 
+    e2e_gaps = []
+
     def e2e_run(n):
         got = 0
+        t_prev = time.perf_counter()
         for res in searcher.serve(reranker, host_batches(n), k, q_rec, topk=k, to_host=(rank == 0)):
             got += 1                                     # rank 0: res = host (ids, scores) of one step
+            t_now = time.perf_counter()
+            e2e_gaps.append(t_now - t_prev)              # host time between consecutive results
+            t_prev = t_now
         assert got == n
 
     e2e_kern = None
@@ -475,6 +481,9 @@ def main():
            "h2d_bytes_per_step": q_host.numel() * q_host.element_size(), "d2h_bytes_per_step": d2h}
     if e2e_kern is not None and e2e_kern[1] > 0:
         e2e["search_kernel_ms"] = e2e_kern[0] / e2e_kern[1]      # the dominant kernel inside the serving loop
+    if len(e2e_gaps) >= args.steps > 2:
+        g_ms = sorted(1e3 * x for x in e2e_gaps[-args.steps + 2:])      # the timed call, without its first results
+        e2e["result_interval_ms"] = {"p50": g_ms[len(g_ms) // 2], "max": g_ms[-1]}
 
     # ---------------- roofline of the dominant kernel (which one: asked from the library) --------
     n_local = hi - lo

@@ -330,8 +330,14 @@ class ShardedSearcher:
         import torch
         dev = torch.device("cuda", self.engine.device)
         s_cmp = torch.cuda.current_stream(dev)
-        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        qd, hout, bufs = [None, None], [None, None], [{}, {}]   # per-slot device buffers: nothing is allocated per step
+        # streams, staging buffers (device and pinned host) and events live on the searcher: a second serve() call
+        # allocates nothing (a pinned allocation costs milliseconds)
+        st = getattr(self, "_serve_state", None)
+        if st is None:
+            st = self._serve_state = {"s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                                      "qd": [None, None], "hout": [None, None], "bufs": [{}, {}]}
+        s_in, s_out, qd, hout, bufs = st["s_in"], st["s_out"], st["qd"], st["hout"], st["bufs"]
+        torch.cuda.current_stream(dev).synchronize()    # buffers of an earlier serve() call are free
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_cmp = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event(blocking=True) for _ in range(2)]

@@ -478,3 +478,57 @@ def test_label_ranking_eval_vs_oracle():
         for key in want:
             assert abs(got[key] - want[key]) < 1e-9, key
         assert table[3, 0] == 0.0
+
+
+def test_cfg1_openi_scale_full_pipeline_vs_oracle(tmp_path):
+    """BASELINE configs[0], the whole path at the reference's own scale and through its own entry points: a
+    7.5k x 1024 fp32 gallery loaded from .npy / .json, 1.5k queries, make_retrieval_engine(...).retrieve(Q, K=10,
+    reranker=, query_id=) (exact search + label / KG rerank, reranker.py weights 0.6 / 0.25 / 0.15), relevance by
+    label overlap (contructGT.py:68-81) and P@k / Recall@k / mAP / MRR / nDCG at k = 5 and 10 (the evaluation loop
+    of Evaluate/retrieval_eval_variants.py:96-122) -- against the oracle run on the same files: exact search
+    (sklearn form) -> OracleReranker.rerank per query -> the oracle metric functions.  The ranked id lists must
+    agree except for swaps between near-equal combined scores, and the metrics to 1e-9 wherever the lists are
+    identical (bit-identical per query then)."""
+    from multi_modal_retrieval_predict_project_b200 import Reranker, make_retrieval_engine, synth
+    from multi_modal_retrieval_predict_project_b200.Evaluate import relevance_lists
+    from multi_modal_retrieval_predict_project_b200.Helpers import per_query_metrics
+    n, nq, d, k = 7500, 1500, 1024, 10
+    g = synth.make_embeddings(n, d, seed=synth.SEED, clustered=True)
+    q = synth.make_embeddings(nq, d, seed=synth.SEED + 1, clustered=True)
+    ids, qids = synth.make_ids(n), synth.make_ids(nq, "t")
+    labels = synth.make_labels(n + nq)
+    names = synth.label_names()
+    csv = synth.write_labels_csv(str(tmp_path / "labels.csv"), ids + qids, labels, names)
+    kg_dir = synth.write_kg(str(tmp_path / "kg"), ids + qids, names)
+    fp, ip = synth.write_gallery(str(tmp_path), "train", g, ids)
+    # ---- device path, reference entry points ----
+    eng = make_retrieval_engine(fp, ip, method="dls", link_threshold=0.5, max_links=10)     # fp32, exact
+    rer = Reranker(kg_dir, csv, device=0)
+    got_ids, got_scores = eng.retrieve(q, K=k, reranker=rer, query_id=qids, rerank_topk=k)
+    rel = relevance_lists(labels[n:], qids, labels[:n], ids, exclude_self=False, device=0)
+    # ---- oracle path ----
+    want_rows, _ = osr.exact_topk(q, g, k)
+    ora = orr.OracleReranker(kg_dir, csv)
+    want_rel = ogt.relevance_lists(labels[n:], qids, labels[:n], ids, exclude_self=False)
+    assert rel == want_rel
+    want_ids = []
+    same = np.zeros(nq, dtype=bool)
+    for i in range(nq):
+        cand = [ids[int(j)] for j in want_rows[i]]
+        res = ora.rerank(qids[i], cand, candidate_embs=g[want_rows[i]], query_emb=q[i], topk=k)
+        want_ids.append([t[0] for t in res])
+        same[i] = got_ids[i] == want_ids[i]
+        if not same[i]:       # only swaps between near-equal combined scores
+            assert sorted(got_ids[i]) == sorted(want_ids[i]), i
+            fin = {t[0]: t[1] for t in res}
+            for a_, b_ in zip(got_ids[i], want_ids[i]):
+                assert abs(fin[a_] - fin[b_]) < 1e-5, (i, a_, b_)
+        assert np.allclose(got_scores[i], sorted((t[1] for t in res), reverse=True), rtol=1e-5, atol=5e-6), i
+    assert same.mean() > 0.99
+    rels = [rel[qid] for qid in qids]
+    for kk in (5, 10):
+        got_t = per_query_metrics(got_ids, rels, kk, device=0)
+        want_t = om.per_query_table(want_ids, rels, kk)
+        assert np.array_equal(got_t[same], want_t[same])
+        assert np.allclose(got_t.mean(axis=0), want_t.mean(axis=0), rtol=0, atol=5e-3)     # near-tie swaps in < 1 % of the queries
+    eng.close(); rer.close()
