@@ -234,12 +234,15 @@ def cpu_reference_run(args, steps, warmup):
 
     for _ in range(max(1, warmup)):
         one_step()
+    t_all = time.perf_counter()
     per = [one_step() for _ in range(max(1, steps))]
+    step_wall_ms = 1e3 * (time.perf_counter() - t_all) / max(1, steps)
     pq = float(np.mean([p[0] for p in per]))
     sample = (f"per step: {bq} queries x {n_s}-row slice (1/{frac} of the gallery; search time scaled x{args.rows / n_s:.0f}) "
               f"through sklearn cosine_similarity + np.argsort, + {'the reference Reranker.rerank' if kind == 'reference' else 'the oracle port of Reranker.rerank'} "
               f"of {args.k} candidates timed on 4 queries; mean over {max(1, steps)} steps; BLAS threads={cores} of {ncpu} host cores")
     return {"value": 1.0 / pq, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+            "sample_step_wall_ms": step_wall_ms, "sample_queries_per_step": bq, "sample_rows": n_s,
             "search_s_per_query_full": float(np.mean([p[1] for p in per])) / bq * (args.rows / n_s),
             "rerank_s_per_query": float(np.mean([p[2] for p in per]))}
 
@@ -332,7 +335,9 @@ def main():
         t0 = time.perf_counter()
         cb = cpu_reference_run(args, args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / cb["value"],
+                # a step of this arm = one bounded sample (cpu_baseline.sample); `value` is the extrapolated full-
+                # gallery rate, ms_per_step the measured wall time of a sample step
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sample_step_wall_ms"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
