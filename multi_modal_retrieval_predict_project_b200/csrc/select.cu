@@ -268,7 +268,9 @@ struct RemoteSink {
     const longlong2* s_row2 = reinterpret_cast<const longlong2*>(o_row);
     for (int v = t; v < s.kp / 4; v += nt) d_sc[v] = s_sc4[v];
     for (int v = t; v < s.kp / 2; v += nt) d_row[v] = s_row2[v];
-    __threadfence_system();  // before the signal kernel's release
+    // one system-scope fence per warp that stored something (<= 75 vectors: the first three warps), not one
+    // per thread of the CTA: the signal kernel's release follows in stream order
+    if (t < ((s.kp / 2 + 31) & ~31)) __threadfence_system();
   }
 };
 
