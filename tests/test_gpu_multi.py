@@ -46,6 +46,16 @@ def _worker(rank, world, port, out_dir):
         assert torch.equal(ids3, want_ids) and torch.equal(fin3, want_fin)
     ids3, fin3 = ids3.clone(), fin3.clone()      # views of the exchange region: it is re-created below (larger K)
     s._px.check()
+    # soak: 400 back-to-back steps with no host synchronisation in between (the double-buffered regions, the flag
+    # protocol and the per-parity counters are reused 200 times each); every 50th result is kept and compared
+    kept = []
+    for it in range(400):
+        a_ids, a_fin = s.retrieve_reranked(rer, qd, k, q_rec, topk=20)
+        if it % 50 == 49:
+            kept.append((a_ids.clone(), a_fin.clone()))
+    torch.cuda.synchronize()
+    s._px.check()
+    assert all(torch.equal(i_, want_ids) and torch.equal(f_, want_fin) for i_, f_ in kept)
     s_nccl = ShardedSearcher(eng, use_peer=False)                                     # same step through NCCL
     ids4, fin4 = s_nccl.retrieve_reranked(rer, qd, k, q_rec, topk=20)
     torch.cuda.synchronize()

@@ -299,6 +299,18 @@ def test_exchange_kernels_on_one_gpu_equal_the_single_shard_path():
             fin = _lib.as_cuda_tensor(p_fin.value, (bb, keep), torch.float64, 0)
             torch.cuda.synchronize()
             assert torch.equal(ids, want_ids) and torch.equal(fin, want_fin), (k, bb, topk, algo)
+    # soak: 300 back-to-back steps of one shape, no host synchronisation in between
+    rows, scores = eng.search(qd, k, algo=algo)
+    want_ids, want_fin = rer.rerank_scored_device(rows, scores, q_rec[:bb].contiguous(), topk)
+    for _ in range(300):
+        step += 1
+        _lib.check(lib.mmr_search_scatter(eng._handle, ex, _lib.ptr(qd), bb, _lib.MMR_F32, k, _lib.ALGOS[algo], step,
+                                          _lib.current_stream(0)))
+        _lib.check(lib.mmr_exchange_rerank(ex, rer._tables, _lib.ptr(q_rec), bb, k, rer.alpha, rer.beta, rer.gamma,
+                                           topk, step, C.byref(p_ids), C.byref(p_fin), _lib.current_stream(0)))
+    torch.cuda.synchronize()
+    assert torch.equal(_lib.as_cuda_tensor(p_ids.value, (bb, keep), torch.int64, 0), want_ids)
+    assert torch.equal(_lib.as_cuda_tensor(p_fin.value, (bb, keep), torch.float64, 0), want_fin)
     code = C.c_int32(-1)
     assert lib.mmr_exchange_status(ex, C.byref(code)) == 0 and code.value == 0
     assert lib.mmr_search_scatter(eng._handle, ex, _lib.ptr(qd), 301, _lib.MMR_F32, 10, 0, step + 1, None) == _lib.MMR_EINVAL
