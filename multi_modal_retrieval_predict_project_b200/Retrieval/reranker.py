@@ -299,11 +299,11 @@ class Reranker:
                         for j, s in zip(order[i], sc[i]) if j >= 0])
         return out
 
-    def rerank_device(self, engine, q_embs, cand_rows, q_rec, cand_rec, topk: int = 0):
+    def rerank_device(self, engine, q_embs, cand_rows, q_rec, cand_rec, topk: int = 0, counts=None):
         """All-device batched rerank (bench / serving path): torch CUDA tensors in and out.
         ``q_embs`` (B, D) fp32, ``cand_rows`` (B, K) int64 global rows, ``q_rec`` (B) and
-        ``cand_rec`` (B, K) int64 record-table rows.  Returns ``(order (B, keep) int32,
-        scores (B, keep, 4) fp64)``."""
+        ``cand_rec`` (B, K) int64 record-table rows, ``counts`` (B) int32 valid candidates per query (default K).
+        Returns ``(order (B, keep) int32, scores (B, keep, 4) fp64)``."""
         import torch
         b, k = cand_rows.shape
         keep = topk if 0 < topk < k else k
@@ -311,7 +311,7 @@ class Reranker:
         sc = torch.empty((b, keep, 4), dtype=torch.float64, device=cand_rows.device)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.mmr_rerank(engine._handle, self._tables, _lib.ptr(q_embs), None,
-                                            _lib.ptr(cand_rows), _lib.ptr(q_rec), _lib.ptr(cand_rec), None, b, k,
+                                            _lib.ptr(cand_rows), _lib.ptr(q_rec), _lib.ptr(cand_rec), _lib.ptr(counts), b, k,
                                             int(q_embs.shape[1]), self.alpha, self.beta, self.gamma, int(topk),
                                             _lib.ptr(order), _lib.ptr(sc), _lib.current_stream(self.device)))
         return order, sc

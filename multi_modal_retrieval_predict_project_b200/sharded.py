@@ -26,6 +26,13 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_total, lo + per)
 
 
+def _valid_counts(rows):
+    """(B,) int32 number of real candidates per query (-1 rows pad a result when the gallery has fewer than K rows):
+    padding must stay out of the rerank's min-max scaling."""
+    import torch
+    return (rows >= 0).sum(dim=1).to(torch.int32).contiguous()
+
+
 def merge_topk(scores, rows, k_out: int, want_src: bool = False):
     """K-way merge of ``(n_lists, B, K_in)`` CUDA tensors -> ``(B, k_out)`` best first (score desc,
     row asc).  With ``want_src`` also returns the flat source position ``list*K_in + j`` of every
@@ -213,13 +220,13 @@ class ShardedSearcher:
         if self.world == 1:
             rows, scores = eng.search(queries, K, algo=algo)
             if getattr(reranker, "emb_feature", "search_score") == "search_score":
-                order, sc = reranker.rerank_with_cos_device(scores, q_rec, rows, topk)
+                order, sc = reranker.rerank_with_cos_device(scores, q_rec, rows, topk, counts=_valid_counts(rows))
             else:
-                order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
+                order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk, counts=_valid_counts(rows))
             return rows, scores, order, sc
         gblob = self._local_blob(reranker, queries, K, algo)
         out_r, out_s, cos = self._merge_slice(gblob, b, K, 0, b)
-        order, sc = reranker.rerank_with_cos_device(cos, q_rec, out_r, topk)
+        order, sc = reranker.rerank_with_cos_device(cos, q_rec, out_r, topk, counts=_valid_counts(out_r))
         return out_r, out_s, order, sc
 
     def retrieve_reranked(self, reranker, queries, K: int, q_rec, topk: int = 0, algo: Optional[str] = None,
@@ -262,9 +269,9 @@ class ShardedSearcher:
             if by_score and reranker.fused_tail_ok(K):
                 return reranker.rerank_scored_device(rows, scores, q_rec, topk)
             if by_score:
-                order, sc = reranker.rerank_with_cos_device(scores, q_rec, rows, topk)
+                order, sc = reranker.rerank_with_cos_device(scores, q_rec, rows, topk, counts=_valid_counts(rows))
             else:
-                order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk)
+                order, sc = reranker.rerank_device(eng, queries, rows, q_rec, rows, topk, counts=_valid_counts(rows))
             ids = torch.empty((b, keep), dtype=torch.int64, device=dev)
             fin = torch.empty((b, keep), dtype=torch.float64, device=dev)
             with torch.cuda.device(d):
@@ -310,7 +317,7 @@ class ShardedSearcher:
                 reranker.rerank_scored_device(out_r, cos, q_rec[q_lo:q_hi], topk,
                                               out=(my_ids[: q_hi - q_lo], my_fin[: q_hi - q_lo]))
             else:
-                order, sc = reranker.rerank_with_cos_device(cos, q_rec[q_lo:q_hi], out_r, topk)
+                order, sc = reranker.rerank_with_cos_device(cos, q_rec[q_lo:q_hi], out_r, topk, counts=_valid_counts(out_r))
                 with torch.cuda.device(d):
                     _lib.check(lib.mmr_apply_order(_lib.ptr(out_r), _lib.ptr(order), _lib.ptr(sc), q_hi - q_lo, K, keep,
                                                    _lib.ptr(my_ids), _lib.ptr(my_fin), d, _lib.current_stream(d)))

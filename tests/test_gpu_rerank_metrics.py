@@ -544,3 +544,33 @@ def test_cfg1_openi_scale_full_pipeline_vs_oracle(tmp_path):
         assert np.array_equal(got_t[same], want_t[same])
         assert np.allclose(got_t.mean(axis=0), want_t.mean(axis=0), rtol=0, atol=5e-3)     # near-tie swaps in < 1 % of the queries
     eng.close(); rer.close()
+
+
+@pytest.mark.parametrize("emb_feature", ["search_score", "recompute"])
+def test_batched_retrieve_unfused_paths_with_padding(emb_feature):
+    """K beyond the fused tail (K = 200 > 128) on a gallery with fewer rows than K: the batched retrieve path
+    falls back to the unfused kernels; the -1 padding of the search result stays out of the min-max scaling
+    (valid-candidate counts are passed) and comes out as id -1.  Both embedding-feature modes, against the oracle
+    restatement on the valid candidates."""
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, synth
+    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher
+    n, d, b, k = 150, 64, 9, 200
+    g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=45, clustered=True))
+    q = osr.to_bf16_round(synth.make_embeddings(b, d, seed=46, clustered=True))
+    masks, kg = _tables(n, b, 48, 47)
+    eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0)
+    rer = Reranker.from_tables(masks, kg, device=0)
+    rer.emb_feature = emb_feature
+    qd = torch.from_numpy(q).cuda()
+    q_rec = torch.arange(n, n + b, device="cuda")
+    ids, fin = ShardedSearcher(eng).retrieve_reranked(rer, qd, k, q_rec, topk=0)
+    rows, _ = eng.search(qd, k)
+    torch.cuda.synchronize()
+    ids_h, fin_h, rows_h = ids.cpu().numpy(), fin.cpu().numpy(), rows.cpu().numpy()
+    assert ids_h.shape == (b, k) and np.all(ids_h[:, n:] == -1) and np.all(fin_h[:, n:] == 0.0)
+    for i in range(b):
+        cand = rows_h[i, :n]
+        want = orr.rerank_from_arrays(q[i], g[cand], masks[n + i], masks[cand], kg[n + i], kg[cand], topk=n)
+        ok, why = orr.reranked_lists_match(ids_h[i, :n], fin_h[i, :n], cand, want)
+        assert ok, (emb_feature, i, why)
