@@ -142,3 +142,46 @@ def test_shard_merge_equals_single_and_exclusion(big):
     rx, sx = eng.search(q[:64], 99, exclude_rows=r[:, 0].contiguous())
     assert torch.equal(rx, r[:, 1:]) and torch.equal(sx, s[:, 1:])
     a.close(); b.close()
+
+
+def test_cfg2_and_cfg5_full_size_vs_oracle(big):
+    """BASELINE configs[1] and [4] at their full sizes on the first 1M rows of the gallery: cfg2 = 1024 queries,
+    top-100 (64 sampled queries against the brute-force oracle); cfg5 = 10k queries, top-100, then P@k / Recall@k /
+    AP / RR / nDCG on the device against CSR relevance sets -- the metric table of 64 queries must be IDENTICAL to
+    the oracle's (fp64, bit for bit), and the searched rows of those queries must match the brute force."""
+    import bench
+    from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine
+    from multi_modal_retrieval_predict_project_b200.Helpers import metrics_from_rows
+    from oracle import metrics as om
+    from oracle.bruteforce import check_topk
+    n, k = 1_000_000, 100
+    g = big["g"][:n]
+    eng = B200RetrievalEngine.from_arrays(g, dtype="bfloat16", device=0, borrow=True, keep_host=False)
+    # cfg2
+    q2 = bench.gen_queries(1024, DIM, torch.device("cuda", 0), seed=bench.SEED + 900_001)
+    rows2, scores2 = eng.search(q2, k)
+    plan = eng.last_plan()
+    assert plan["algo"] == "gemm" and plan["pair"] and plan["variant"] == "short", plan
+    sel = torch.arange(0, 1024, 16, device="cuda") + torch.arange(64, device="cuda") % 16
+    ok, detail = check_topk(rows2[sel], scores2[sel], g, q2[sel], k)
+    assert ok, detail
+    # cfg5
+    nq = 10_000
+    q5 = bench.gen_queries(nq, DIM, torch.device("cuda", 0), seed=bench.SEED + 900_002)
+    rows5, scores5 = eng.search(q5, k)
+    rows_h = rows5.cpu().numpy()
+    rng = np.random.default_rng(bench.SEED + 1)
+    sizes = rng.integers(1, 201, size=nq)
+    sets = [np.union1d(rng.choice(n, size=int(sizes[i]), replace=False), rows_h[i, (i % 3)::3]) for i in range(nq)]
+    indptr = np.zeros(nq + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum([len(x) for x in sets])
+    rel = np.concatenate(sets).astype(np.int64)
+    tbl = metrics_from_rows(rows5, torch.from_numpy(indptr).cuda(), torch.from_numpy(rel).cuda(), k).cpu().numpy()
+    chk = np.arange(0, nq, nq // 64)[:64]
+    want = om.per_query_table([[int(x) for x in rows_h[i]] for i in chk], [sets[i].tolist() for i in chk], k)
+    assert np.array_equal(tbl[chk], want)
+    assert 0.2 < tbl[:, 0].mean() < 0.5 and tbl[:, 4].mean() > 0.5          # the relevance sets are not degenerate
+    ok, detail = check_topk(rows5[torch.from_numpy(chk).cuda()], scores5[torch.from_numpy(chk).cuda()], g,
+                            q5[torch.from_numpy(chk).cuda()], k)
+    assert ok, detail
+    eng.close()
