@@ -493,7 +493,8 @@ def main():
     # ---------------- roofline of the dominant kernel (which one: asked from the library) --------
     n_local = hi - lo
     kern_avg_ms = kern_ms / max(kern_n, 1)
-    per_rank = torch.tensor([kern_avg_ms, my_ms / args.steps], device=dev, dtype=torch.float64)
+    per_rank = torch.tensor([kern_avg_ms, my_ms / args.steps, float(clocks.get("sm_mhz") or 0),
+                             float("sw_power_cap" in clocks.get("reasons", []))], device=dev, dtype=torch.float64)
     all_ranks = [torch.zeros_like(per_rank) for _ in range(world)]
     if world > 1:
         dist.all_gather(all_ranks, per_rank)
@@ -539,6 +540,9 @@ def main():
         roofline["kernel_ms_by_rank"] = {"min": min(kern_by_rank), "max": max(kern_by_rank)}
         roofline["step_ms_by_rank"] = {"min": min(step_by_rank), "max": max(step_by_rank)}
         roofline["outside_kernel_ms"] = elapsed_ms / args.steps - max(kern_by_rank)
+        # rank skew of the same-sized shard launches is a clock difference between the GPUs when these differ
+        roofline["by_rank"] = [{"rank": r, "kernel_ms": float(t[0]), "sm_mhz": int(t[2]), "sw_power_cap": bool(t[3])}
+                               for r, t in enumerate(all_ranks)]
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
