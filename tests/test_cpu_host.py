@@ -88,6 +88,22 @@ def test_shard_bounds_cover_rows():
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
 
 
+def test_weighted_shard_bounds():
+    from multi_modal_retrieval_predict_project_b200.sharded import shard_bounds, weighted_shard_bounds
+    for n, w in ((10_000_000, [1.0, 1.08]), (10_000_000, [3.4, 3.6, 3.5, 3.55, 3.5, 3.5, 3.6, 3.52]), (1000, [1, 1, 1]),
+                 (5, [1.0] * 8), (0, [1, 2]), (777, [0, 1, 0])):
+        b = [weighted_shard_bounds(n, w, r) for r in range(len(w))]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] and b[i][0] <= b[i][1] for i in range(len(w) - 1))
+        assert all(x[1] % 256 == 0 for x in b[:-1])
+        if n >= 1_000_000:      # proportional to within a tile
+            tot = sum(w)
+            assert all(abs((hi - lo) - n * wi / tot) <= 256 for (lo, hi), wi in zip(b, w))
+    # equal weights = equal shards up to the tile alignment; no weights at all = the plain split
+    assert weighted_shard_bounds(1 << 20, [2.0, 2.0], 0) == shard_bounds(1 << 20, 2, 0)
+    assert weighted_shard_bounds(1001, [0.0, 0.0], 1) == shard_bounds(1001, 2, 1)
+
+
 def test_create_dump_embedding_matches_reference(tmp_path):
     """createDumpEmbedding writes the reference's merged files (Helpers/dumpEmbedding.py:28-39); when the
     reference is mounted its own function is run on a copy of the inputs and the outputs compared."""

@@ -17,7 +17,7 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from multi_modal_retrieval_predict_project_b200 import B200RetrievalEngine, Reranker, synth
-    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher, shard_bounds
+    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher, weighted_shard_bounds
     from oracle import search as osr
     n, d, b, k = 40001, 256, 70, 50
     g = osr.to_bf16_round(synth.make_embeddings(n, d, seed=5))
@@ -26,7 +26,8 @@ def _worker(rank, world, port, out_dir):
     masks = rng.integers(0, 2 ** 43, size=n + b, dtype=np.uint64) & rng.integers(0, 2 ** 43, size=n + b, dtype=np.uint64)
     kg = rng.standard_normal((n + b, 64)).astype(np.float32)
     kg /= np.linalg.norm(kg, axis=1, keepdims=True) + 1e-12
-    lo, hi = shard_bounds(n, world, rank)
+    # unequal shards (sized by a per-GPU rate, as bench.py does at N > 1): global rows = local + offset either way
+    lo, hi = weighted_shard_bounds(n, [1.0 + 0.15 * ((r * 5) % 3) for r in range(world)], rank)
     eng = B200RetrievalEngine.from_arrays(g[lo:hi], dtype="bfloat16", device=rank, row_offset=lo)
     rer = Reranker.from_tables(masks, kg, device=rank)
     s = ShardedSearcher(eng)
