@@ -509,9 +509,9 @@ def main():
         pass
 
     def traffic_for(kernel, rows, batch, kk):
-        t = traffic_tbl.get(kernel)
-        if t and (t["rows"], t["dim"], t["batch"], t["k"]) == (rows, args.dim, batch, kk):
-            return t["bytes"]
+        for t in traffic_tbl.get(kernel) or []:      # one entry per captured shape
+            if (t["rows"], t["dim"], t["batch"], t["k"]) == (rows, args.dim, batch, kk):
+                return t["bytes"]
         return None
 
     def gemm_roofline(flops, ms, pl, rows, batch, kk, in_long_step=True):

@@ -4,6 +4,7 @@
     python profiles/summarize.py launches gpurun_out/launches_r1.csv  > profiles/r1_launches.md
     python profiles/summarize.py kernel  gpurun_out/prof_r1_gemm.ncu-rep gemm_topk > profiles/r1_gemm_topk.md
     python profiles/summarize.py traffic gemm_topk_kernel:gpurun_out/prof_r2_gemm_long.ncu-rep:10000000:512:4096:100 \
+                                         gemm_topk_kernel:gpurun_out/prof_r2_gemm_short.ncu-rep:1250000:512:4096:100 \
                                          scan_topk_kernel:gpurun_out/prof_r2_scan.ncu-rep:10000000:512:1:10 > profiles/traffic.json
 """
 import collections
@@ -115,8 +116,9 @@ def traffic(specs):
         idx = {h: i for i, h in enumerate(hdr)}
         r = [x for x in rws[2:] if name.split("_kernel")[0] in x[idx['Kernel Name']]][0]
         tot = sum(float(r[idx[m]].replace(',', '')) * mult[units[idx[m]]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
-        out[name] = {"rows": int(rows), "dim": int(dim), "batch": int(batch), "k": int(k), "bytes": int(tot),
-                     "kernel": r[idx['Kernel Name']][:80], "source": rep.split('/')[-1]}
+        out.setdefault(name, []).append({"rows": int(rows), "dim": int(dim), "batch": int(batch), "k": int(k),
+                                         "bytes": int(tot), "kernel": r[idx['Kernel Name']][:80],
+                                         "source": rep.split('/')[-1]})
     print(json.dumps(out, indent=2))
 
 
