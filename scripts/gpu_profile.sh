@@ -23,7 +23,7 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_topk_kernel
     -o $out/prof_${tag}_gemm_short -f python bench.py $one --rows 1250000 > $out/ncu_gemm_short_$tag.log 2>&1
 echo "ncu gemm short exit=$?"
 # the tail of a step: selection kernel and the fused rerank tail (4th launch of each)
-ncu --set full --clock-control none --import-source on -k regex:select_fast_kernel --launch-skip 3 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:select_warp_kernel --launch-skip 3 -c 1 \
     -o $out/prof_${tag}_select -f python bench.py $one > $out/ncu_select_$tag.log 2>&1
 echo "ncu select exit=$?"
 ncu --set full --clock-control none --import-source on -k regex:rerank_scored_kernel --launch-skip 3 -c 1 \
