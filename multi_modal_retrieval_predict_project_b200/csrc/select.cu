@@ -5,8 +5,13 @@
 // lists (from the scan CTAs, the GEMM CTAs, or the per-GPU lists after the NCCL all-gather) produce
 // the global top-K per query, best first, ordered by (score desc, row asc).
 //
-// One CTA per query; candidates are packed 64-bit keys sorted with a shared-memory bitonic network.
-// More candidates than fit (8192 keys) are consumed in rounds that keep the running top-K.
+// Three kernels, all on packed 64-bit keys (ordered score, inverted row: score desc, row asc):
+//   select_warp_kernel  one WARP per query over the GEMM's per-(query, list) candidate lists, k <= 128 -- the
+//                       selection of every batched search step (and, with RemoteSink, its multi-GPU scatter);
+//   select_fast_kernel  one CTA per query, <= 4096 candidate slots, k <= 128 (merge of per-GPU / per-scan-CTA
+//                       lists; two passes above 4096 slots);
+//   select_topk_kernel  one CTA per query, any k <= 1024: shared-memory bitonic network, more candidates than
+//                       fit (8192 keys) are consumed in rounds that keep the running top-K.
 // Latency/launch-bound, tiny next to the search kernels (reported as time only).
 #include "internal.h"
 

@@ -350,6 +350,37 @@ def test_exclusion_at_max_k_and_tune_errors():
         eng.tune(variant="medium")
 
 
+@pytest.mark.parametrize("n,parts,pair,k,exclude", [(9000, 12, 0, 128, False), (9000, 12, 1, 128, True),
+                                                    (20000, 30, 1, 100, False), (3000, 16, 0, 127, True)])
+def test_selection_over_many_full_lists(n, parts, pair, k, exclude):
+    """The warp-per-query selection with more valid candidates than a warp holds: many gallery parts of a few
+    hundred rows each leave up to k (k + 1 with an exclusion) entries per list and no published pruning bound, so
+    the warp cuts its 512-key buffer back to the top-k several times per query (csrc/select.cu
+    select_warp_kernel / warp_keep_topk).  Duplicated gallery rows put exact score ties across the cuts."""
+    from multi_modal_retrieval_predict_project_b200 import synth
+    g = osr.to_bf16_round(synth.make_embeddings(n, 64, seed=181 + parts, clustered=True))
+    g[n // 2:n // 2 + 200] = g[:200]                      # exact duplicates in another part
+    q = osr.to_bf16_round(synth.make_embeddings(70, 64, seed=182, clustered=True))
+    q[:8] = g[:8]
+    eng = _engine(g, dtype="bfloat16")
+    try:
+        eng.tune(parts=parts, pair=pair)
+    except NotImplementedError:
+        pytest.skip("plan not available")
+    ex = np.arange(70, dtype=np.int64) if exclude else None
+    rows, scores = eng.search(q, k, exclude_rows=ex, algo="gemm")
+    plan = eng.last_plan()
+    assert plan["algo"] == "gemm" and plan["parts"] >= 2
+    sim = osr.cosine_similarity(q, g)
+    if exclude:
+        sim[np.arange(70), ex] = -np.inf
+    for i in range(70):
+        order = np.lexsort((np.arange(n), -sim[i].astype(np.float64)))[:k]
+        ok, why = osr.topk_matches(rows[i], scores[i], order, sim[i, order], rtol=2e-5, atol=1e-6)
+        assert ok, (i, why)
+        assert len(set(rows[i].tolist())) == k
+
+
 def test_two_streams_one_handle_are_ordered_on_the_device():
     """Two streams (and two host threads) searching through ONE handle with device outputs: the handle's
     workspaces are shared, so the library orders the calls on the device (an event recorded at the end
