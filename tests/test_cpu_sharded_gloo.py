@@ -40,14 +40,14 @@ def _cpu_merge(scores, rows, k_out):
     return torch.from_numpy(out_r), torch.from_numpy(out_s)
 
 
-def _worker(rank, world, port, n, d, b, k, out_dir):
+def _worker(rank, world, port, n, d, b, k, out_dir, weights=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from multi_modal_retrieval_predict_project_b200 import synth
-    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher, shard_bounds
+    from multi_modal_retrieval_predict_project_b200.sharded import ShardedSearcher, shard_bounds, weighted_shard_bounds
     g = synth.make_embeddings(n, d, seed=3)
     q = synth.make_embeddings(b, d, seed=4)
-    lo, hi = shard_bounds(n, world, rank)
+    lo, hi = shard_bounds(n, world, rank) if weights is None else weighted_shard_bounds(n, weights, rank, align=8)
     s = ShardedSearcher(_OracleShardEngine(g[lo:hi], lo), merge=_cpu_merge)
     assert s.world == world
     rows, scores = s.search(torch.from_numpy(q), k)
@@ -56,12 +56,13 @@ def _worker(rank, world, port, n, d, b, k, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,k", [(1001, 10), (37, 25)])
-def test_sharded_search_plumbing_world2(tmp_path, n, k):
+@pytest.mark.parametrize("n,k,weights", [(1001, 10, None), (37, 25, None), (1001, 10, [1.0, 2.5]), (37, 25, [0.0, 1.0])])
+def test_sharded_search_plumbing_world2(tmp_path, n, k, weights):
+    """world-2 gloo run of the sharded search plumbing: equal shards, unequal (weighted) shards, an EMPTY shard."""
     world, d, b = 2, 32, 9
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, n, d, b, k, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, d, b, k, str(tmp_path), weights), nprocs=world, join=True)
     from multi_modal_retrieval_predict_project_b200 import synth
     g = synth.make_embeddings(n, d, seed=3); q = synth.make_embeddings(b, d, seed=4)
     want_rows, want_scores = osr.exact_topk(q, g, k)
