@@ -381,6 +381,26 @@ def test_selection_over_many_full_lists(n, parts, pair, k, exclude):
         assert len(set(rows[i].tolist())) == k
 
 
+def test_empty_shard_returns_padding():
+    """A shard without rows (more ranks than gallery tiles: sharded.shard_bounds / weighted_shard_bounds can hand a
+    rank an empty block) answers every query with -1 / -inf padding, which the cross-shard merge ignores."""
+    import torch
+    from multi_modal_retrieval_predict_project_b200 import synth
+    from multi_modal_retrieval_predict_project_b200.sharded import merge_topk
+    eng = _engine(np.zeros((0, 64), dtype=np.float32), dtype="bfloat16", row_offset=1234)
+    q = osr.to_bf16_round(synth.make_embeddings(5, 64, seed=191))
+    rows, scores = eng.search(q, 7)
+    assert rows.shape == (5, 7) and np.all(rows == -1) and np.all(np.isneginf(scores))
+    qd = torch.from_numpy(q).cuda()
+    r_d, s_d = eng.search(qd, 7)
+    assert bool((r_d == -1).all()) and bool(torch.isneginf(s_d).all())
+    g = osr.to_bf16_round(synth.make_embeddings(300, 64, seed=192))
+    full = _engine(g, dtype="bfloat16")
+    r_f, s_f = full.search(qd, 7)
+    m_r, m_s = merge_topk(torch.stack([s_f, s_d]), torch.stack([r_f, r_d]), 7)
+    assert torch.equal(m_r, r_f) and torch.equal(m_s, s_f)
+
+
 def test_two_streams_one_handle_are_ordered_on_the_device():
     """Two streams (and two host threads) searching through ONE handle with device outputs: the handle's
     workspaces are shared, so the library orders the calls on the device (an event recorded at the end
