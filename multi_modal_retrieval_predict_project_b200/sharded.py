@@ -29,7 +29,7 @@ def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
 def weighted_shard_bounds(n_total: int, weights, rank: int, align: int = 256) -> Tuple[int, int]:
     """Contiguous row block of ``rank`` when the blocks are sized in proportion to ``weights`` (unequal devices,
     or ranks that also hold other data).  Interior cuts are multiples of ``align`` rows (the search kernel's
-    tile); every rank computes the same cuts from the same weights.  Global row = local row + block start, as
+    tile) or the end of the gallery; every rank computes the same cuts from the same weights.  Global row = local row + block start, as
     with :func:`shard_bounds`.  bench.py keeps equal blocks: the kernel-time differences between the GPUs of one
     box (1-4 %) change sign between a calibration run and the timed run (measured at N = 2), so there is nothing
     stable to weight by."""
@@ -40,7 +40,7 @@ def weighted_shard_bounds(n_total: int, weights, rank: int, align: int = 256) ->
     cuts, acc = [0], 0.0
     for x in w[:-1]:
         acc += x
-        c = int(round(n_total * acc / tot / align)) * align
+        c = n_total if acc >= tot else int(round(n_total * acc / tot / align)) * align   # nothing left for the rest
         cuts.append(min(n_total, max(cuts[-1], c)))
     cuts.append(n_total)
     return cuts[rank], cuts[rank + 1]

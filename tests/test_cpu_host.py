@@ -95,13 +95,15 @@ def test_weighted_shard_bounds():
         b = [weighted_shard_bounds(n, w, r) for r in range(len(w))]
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] and b[i][0] <= b[i][1] for i in range(len(w) - 1))
-        assert all(x[1] % 256 == 0 for x in b[:-1])
+        assert all(x[1] % 256 == 0 or x[1] == n for x in b[:-1])
         if n >= 1_000_000:      # proportional to within a tile
             tot = sum(w)
             assert all(abs((hi - lo) - n * wi / tot) <= 256 for (lo, hi), wi in zip(b, w))
     # equal weights = equal shards up to the tile alignment; no weights at all = the plain split
     assert weighted_shard_bounds(1 << 20, [2.0, 2.0], 0) == shard_bounds(1 << 20, 2, 0)
     assert weighted_shard_bounds(1001, [0.0, 0.0], 1) == shard_bounds(1001, 2, 1)
+    # a rank with all the weight holds every row (no remainder of the tile alignment leaks to the next rank)
+    assert [weighted_shard_bounds(40001, [1.0, 0.0, 0.0], r) for r in range(3)] == [(0, 40001), (40001, 40001), (40001, 40001)]
 
 
 def test_create_dump_embedding_matches_reference(tmp_path):

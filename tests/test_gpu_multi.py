@@ -79,6 +79,20 @@ def _worker(rank, world, port, out_dir):
     g_ids, g_fin = s_nccl.retrieve_reranked(rer, qd[:9].contiguous(), 200, q_rec[:9].contiguous(), topk=0)
     torch.cuda.synchronize()
     assert torch.equal(f_ids, g_ids) and torch.equal(f_fin, g_fin)
+    # all rows on rank 0, EMPTY shards elsewhere (more GPUs than data): both transports, same answer
+    lo_e, hi_e = weighted_shard_bounds(n, [1.0] + [0.0] * (world - 1), rank)
+    assert (hi_e - lo_e) == (n if rank == 0 else 0)
+    eng_e = B200RetrievalEngine.from_arrays(g[lo_e:hi_e], dtype="bfloat16", device=rank, row_offset=lo_e)
+    s_e = ShardedSearcher(eng_e)
+    e_ids, e_fin = s_e.retrieve_reranked(rer, qd, k, q_rec, topk=20)
+    torch.cuda.synchronize()
+    assert getattr(s_e, "_px", None) is not None
+    s_e._px.check()
+    assert torch.equal(e_ids, want_ids) and torch.equal(e_fin, want_fin)
+    n_ids, n_fin = ShardedSearcher(eng_e, use_peer=False).retrieve_reranked(rer, qd, k, q_rec, topk=20)
+    torch.cuda.synchronize()
+    assert torch.equal(n_ids, want_ids) and torch.equal(n_fin, want_fin)
+    s_e.close()
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), rows=rows.cpu().numpy(), scores=scores.cpu().numpy(),
              order=order.cpu().numpy(), sc=sc.cpu().numpy(), ids=ids3.cpu().numpy(), fin=fin3.cpu().numpy())
     if rank == 0:  # single-shard reference on the same device
