@@ -434,7 +434,7 @@ select_fast_kernel(Source src, Bound bound, int k_out, int64_t row_offset, Sink 
 #define MMR_SELECT_WARP 1
 #endif
 #ifndef MMR_SELECT_WARP_CTAS
-#define MMR_SELECT_WARP_CTAS 5   // 79 registers, 20 queries in flight per SM (measured: 5 -> 34 us, 6 -> 42, 8 -> 36 for 4096 queries x 9 lists)
+#define MMR_SELECT_WARP_CTAS 5   // register cap 102: 72 (dense sink) / 84 (peer sink) used, no spills; measured for 4096 queries x 18 lists: 5 -> 34 us, 6 -> 42, 8 (64 registers) -> 36
 #endif
 constexpr int kWsCap = 512;   // keys a warp holds (16 per lane in the cut)
 constexpr int kWsWarps = 4;   // queries per CTA
