@@ -25,3 +25,17 @@ def test_reference_arm_json_contract():
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_traffic_table_schema():
+    """profiles/traffic.json (ncu dram__bytes per launch, read by bench.py's roofline.traffic): one LIST of captured
+    shapes per kernel, each with the workload it was captured on; the headline shape must be present."""
+    tbl = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    kernels = {k: v for k, v in tbl.items() if not k.startswith("_")}
+    assert {"gemm_topk_kernel", "scan_topk_kernel"} <= set(kernels)
+    for name, entries in kernels.items():
+        assert isinstance(entries, list) and entries, name
+        for e in entries:
+            assert {"rows", "dim", "batch", "k", "bytes", "source"} <= set(e), (name, e)
+            assert e["bytes"] >= e["rows"] * e["dim"] * 2      # at least one pass over the bf16 gallery
+    assert any((e["rows"], e["dim"], e["batch"], e["k"]) == (10_000_000, 512, 4096, 100) for e in kernels["gemm_topk_kernel"])
